@@ -1,0 +1,465 @@
+// engine.cu -- planner / executor: turns go-dsp's transforms into sequences of passes.
+#include "engine.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pass_launch.cuh"
+
+namespace gd {
+
+// ------------------------------------------------------------------ errors
+std::atomic<long long> g_launches{0};
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+Status cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return e == cudaErrorMemoryAllocation ? GD_ERR_NOMEM : GD_ERR_CUDA;
+}
+static Status invalid(const char* msg) { g_err = msg; return GD_ERR_INVALID; }
+
+static inline int ilog2ll(long long v) { int r = 0; while (v > 1) { v >>= 1; r++; } return r; }
+static inline bool is_pow2(long long x) { return (x & (x - 1)) == 0; }
+
+// ------------------------------------------------------------------ tables
+// exp(-2 pi i e / M) for e = e0, e0+step, ... (count entries), long-double accurate, exact on the axes
+static void host_twiddles(std::vector<cpx>& out, long long M, long long step, long long count) {
+    out.resize((size_t)count);
+    for (long long j = 0; j < count; j++) {
+        long long e = (j * step) % M;
+        long double c, s;
+        if (e == 0) { c = 1; s = 0; }
+        else if (4 * e == M) { c = 0; s = 1; }
+        else if (2 * e == M) { c = -1; s = 0; }
+        else if (4 * e == 3 * M) { c = 0; s = -1; }
+        else {
+            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)e / (long double)M;
+            c = cosl(a); s = sinl(a);
+        }
+        out[(size_t)j] = make_double2((double)c, (double)(-s));
+    }
+}
+
+static Status upload(const std::vector<cpx>& h, cpx** dptr) {
+    GD_CUDA(cudaMalloc((void**)dptr, h.size() * sizeof(cpx)));
+    GD_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+    return GD_OK;
+}
+
+Status Device::init(int device) {
+    std::lock_guard<std::recursive_mutex> lk(mu);
+    if (ready) return GD_OK;
+    dev = device;
+    GD_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    GD_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        set_error("go-dsp_b200 is built for sm_100a (B200) only; device '" + std::string(prop.name) + "' is sm_" +
+                  std::to_string(prop.major) + std::to_string(prop.minor));
+        return GD_ERR_UNSUPPORTED;
+    }
+    num_sms = prop.multiProcessorCount;
+    GD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    GD_CUDA(cudaStreamCreateWithFlags(&stream_in, cudaStreamNonBlocking));
+    GD_CUDA(cudaStreamCreateWithFlags(&stream_out, cudaStreamNonBlocking));
+    for (int k = 5; k <= 12; k++) {
+        std::vector<cpx> h;
+        host_twiddles(h, 1LL << k, 1, 1LL << k);
+        GD_TRY(upload(h, &wl[k]));
+    }
+    if (const char* s = getenv("GD_PASS_SCRATCH_MB")) {
+        long v = atol(s);
+        if (v > 0) pass_scratch_budget = (size_t)v << 20;
+    }
+    if (const char* s = getenv("GD_WIDE_TILES")) wide_tiles = atoi(s) != 0;
+    ready = true;
+    return GD_OK;
+}
+
+void Device::destroy() {
+    std::lock_guard<std::recursive_mutex> lk(mu);
+    if (!ready) return;
+    cudaSetDevice(dev);
+    cudaDeviceSynchronize();
+    for (auto& w : wl) { if (w) cudaFree(w); w = nullptr; }
+    for (auto& kv : tw) { cudaFree(kv.second.lo); if (kv.second.hi) cudaFree(kv.second.hi); }
+    tw.clear();
+    for (auto& kv : blue) { cudaFree(kv.second.chirp_inv); cudaFree(kv.second.bhat); }
+    blue.clear();
+    for (int i = 0; i < SCR_NSLOTS; i++) { if (scratch[i]) cudaFree(scratch[i]); scratch[i] = nullptr; scratch_bytes[i] = 0; }
+    cudaStreamDestroy(stream); cudaStreamDestroy(stream_in); cudaStreamDestroy(stream_out);
+    stream = stream_in = stream_out = nullptr;
+    ready = false;
+}
+
+Status Device::ensure_scratch(ScratchSlot s, size_t bytes, void** out) {
+    if (scratch_bytes[s] < bytes) {
+        if (scratch[s]) {
+            GD_CUDA(cudaDeviceSynchronize());     // nobody may still be using the old block
+            GD_CUDA(cudaFree(scratch[s]));
+            scratch[s] = nullptr; scratch_bytes[s] = 0;
+        }
+        size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        GD_CUDA(cudaMalloc(&scratch[s], want));
+        scratch_bytes[s] = want;
+    }
+    *out = scratch[s];
+    return GD_OK;
+}
+
+Status Device::twiddles(int log2m, TwiddleTable* out) {
+    auto it = tw.find(log2m);
+    if (it == tw.end()) {
+        if (log2m > 24) return invalid("twiddle table: M > 2^24 not supported");
+        long long M = 1LL << log2m;
+        TwiddleTable t;
+        std::vector<cpx> h;
+        host_twiddles(h, M, 1, M < 4096 ? M : 4096);
+        GD_TRY(upload(h, &t.lo));
+        if (log2m > 12) {
+            host_twiddles(h, M, 4096, M >> 12);
+            GD_TRY(upload(h, &t.hi));
+        }
+        it = tw.emplace(log2m, t).first;
+    }
+    *out = it->second;
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------ pass dispatch
+static Status launch_pass(Device& d, int log2l, const PassParams& p, cudaStream_t st) {
+    bool generic = (p.ld_flags & (LD_REAL | LD_PAD | LD_MULAUX | LD_REVERSE)) ||
+                   (p.st_flags & (ST_MULAUX | ST_DIV | ST_TRUNC));
+    cudaError_t e;
+    if (log2l >= 1 && log2l <= 8) e = launch_pass_small(log2l, p, generic, d.num_sms, st);
+    else if (log2l <= 10) e = launch_pass_mid(log2l, d.wide_tiles, p, generic, d.num_sms, st);
+    else if (log2l <= 12) e = launch_pass_big(log2l, d.wide_tiles, p, generic, d.num_sms, st);
+    else return invalid("launch_pass: line length out of range");
+    if (e != cudaSuccess) return cuda_fail(e, "fft_pass_kernel launch");
+    g_launches++;
+    return GD_OK;
+}
+
+static PassParams base_params(Device& d, int log2l) {
+    PassParams p;
+    memset(&p, 0, sizeof(p));
+    p.inner = 1;
+    p.scale = 1.0; p.div = 1.0;
+    p.wl = log2l >= 5 ? d.wl[log2l] : nullptr;
+    return p;
+}
+
+// ------------------------------------------------------------------ power-of-two transforms
+Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, int log2n,
+                long long batch, const FusedOps& ops, cudaStream_t st) {
+    if (log2n < 1 || batch < 1) return invalid("fft_pow2: bad size");
+    const long long N = 1LL << log2n;
+    if (log2n <= 12) {
+        PassParams p = base_params(d, log2n);
+        p.in = in; p.out = out; p.nlines = batch; p.inner = 1;
+        p.in_qs = in_dist; p.in_is = 0; p.in_es = 1;
+        p.out_qs = out_dist; p.out_is = 0; p.out_es = 1;
+        p.in_mode = p.out_mode = MODE_ROW;
+        p.ld_flags = ops.ld_flags; p.st_flags = ops.st_flags;
+        p.aux_in = ops.aux_in; p.aux_out = ops.aux_out;
+        p.n_valid_in = ops.n_valid_in; p.n_valid_out = ops.n_valid_out;
+        p.scale = ops.scale; p.div = ops.div;
+        return launch_pass(d, log2n, p, st);
+    }
+    if (log2n > 24) return invalid("fft_pow2: N > 2^24 needs the multi-GPU path");
+    // four-step: N = N1 * N2, n = n1*N2 + n2, k = k1 + N1*k2
+    const int l1 = (log2n + 1) / 2, l2 = log2n - l1;
+    const long long N1 = 1LL << l1, N2 = 1LL << l2;
+    TwiddleTable tw;
+    GD_TRY(d.twiddles(log2n, &tw));
+    long long chunk = (long long)(d.pass_scratch_budget / ((size_t)N * sizeof(cpx)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    cpx* scr;
+    GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)chunk * N * sizeof(cpx), (void**)&scr));
+    const bool real_in = ops.ld_flags & LD_REAL;
+    for (long long b0 = 0; b0 < batch; b0 += chunk) {
+        long long nb = batch - b0 < chunk ? batch - b0 : chunk;
+        // pass 1: columns n2 of every transform, length N1, twiddle w_N^(n2*k1) on store
+        PassParams p = base_params(d, l1);
+        p.in = real_in ? (const void*)((const double*)in + b0 * in_dist) : (const void*)((const cpx*)in + b0 * in_dist);
+        p.out = scr;
+        p.nlines = nb * N2; p.inner = N2;
+        p.in_qs = in_dist; p.in_is = 1; p.in_es = N2;
+        p.out_qs = N; p.out_is = 1; p.out_es = N2;
+        p.in_mode = p.out_mode = MODE_COL;
+        p.ld_flags = ops.ld_flags; p.aux_in = ops.aux_in; p.n_valid_in = ops.n_valid_in;
+        p.st_flags = ST_TWIDDLE; p.tw_sel = 0; p.tw_log2m = log2n; p.tw_lo = tw.lo; p.tw_hi = tw.hi;
+        GD_TRY(launch_pass(d, l1, p, st));
+        // pass 2: rows k1, length N2, transposed store X[k1 + N1*k2]
+        PassParams r = base_params(d, l2);
+        r.in = scr; r.out = out + b0 * out_dist;
+        r.nlines = nb * N1; r.inner = N1;
+        r.in_qs = N; r.in_is = N2; r.in_es = 1;
+        r.out_qs = out_dist; r.out_is = 1; r.out_es = N1;
+        r.in_mode = MODE_ROW; r.out_mode = MODE_COL;
+        r.st_flags = ops.st_flags; r.aux_out = ops.aux_out; r.n_valid_out = ops.n_valid_out;
+        r.scale = ops.scale; r.div = ops.div;
+        GD_TRY(launch_pass(d, l2, r, st));
+    }
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------ small helper kernels
+__global__ void copy1_kernel(const void* in, long long in_dist, cpx* out, long long out_dist, long long batch, int real_in) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    cpx v;
+    if (real_in) v = make_double2(((const double*)in)[b * in_dist], 0.0);
+    else v = ((const cpx*)in)[b * in_dist];
+    out[b * out_dist] = v;
+}
+
+// chirp tables with the reference's exact argument arithmetic (fft/bluestein.go:48-57):
+// arg = fl(fl(pi / N) * fl(i*i)); i*i is exact in int64 and in double for N < 9.4e7.
+__global__ void chirp_kernel(long long n, long long la, cpx* chirp_inv, cpx* b) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c;
+    if (i == 0) { s = 0.0; c = 1.0; }
+    else {
+        double coef = __ddiv_rn(3.14159265358979323846, (double)n);
+        double arg = __dmul_rn(coef, (double)(i * i));
+        sincos(arg, &s, &c);
+    }
+    chirp_inv[i] = make_double2(c, -s);
+    b[i] = make_double2(c, s);
+    if (i != 0) b[la - i] = make_double2(c, s);
+}
+
+__global__ void pointwise_mul_kernel(cpx* a, const cpx* b, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = cmul(a[i], b[i]);
+}
+
+// lines (o, i) of length len and element stride s  <->  dense [line][len]
+__global__ void gather_lines_kernel(const cpx* src, cpx* dst, long long line0, long long nlines, long long len, long long s) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= nlines * len) return;
+    long long l = t / len, j = t - l * len;
+    long long line = line0 + l, o = line / s, i = line - o * s;
+    dst[t] = src[o * len * s + i + j * s];
+}
+__global__ void scatter_lines_kernel(const cpx* src, cpx* dst, long long line0, long long nlines, long long len, long long s) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= nlines * len) return;
+    long long l = t / len, j = t - l * len;
+    long long line = line0 + l, o = line / s, i = line - o * s;
+    dst[o * len * s + i + j * s] = src[t];
+}
+
+__global__ void splitmix_kernel(double* out, long long n, unsigned long long seed, unsigned long long offset) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = splitmix_unit(seed, offset + (unsigned long long)i);
+}
+
+static inline unsigned grid_for(long long n, int block) {
+    long long g = (n + block - 1) / block;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+Status fill_splitmix(double* out, long long n, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
+    if (n <= 0) return GD_OK;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    splitmix_kernel<<<(unsigned)g, 256, 0, st>>>(out, n, seed, offset);
+    g_launches++;
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------ Bluestein
+Status Device::bluestein(long long n, cudaStream_t st, const BluesteinPlan** out) {
+    auto it = blue.find(n);
+    if (it == blue.end()) {
+        BluesteinPlan pl;
+        pl.n = n;
+        long long need = 2 * n - 1;                 // dsputils.NextPowerOf2(2N-1), dsputils/dsputils.go:39-45
+        pl.la = 1; pl.log2la = 0;
+        while (pl.la < need) { pl.la <<= 1; pl.log2la++; }
+        if (pl.log2la > 24) return invalid("bluestein: padded length > 2^24 not supported");
+        GD_CUDA(cudaMalloc((void**)&pl.chirp_inv, (size_t)n * sizeof(cpx)));
+        GD_CUDA(cudaMalloc((void**)&pl.bhat, (size_t)pl.la * sizeof(cpx)));
+        cpx* b;
+        GD_TRY(ensure_scratch(SCR_AUX, (size_t)pl.la * sizeof(cpx), (void**)&b));
+        GD_CUDA(cudaMemsetAsync(b, 0, (size_t)pl.la * sizeof(cpx), st));
+        chirp_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, pl.la, pl.chirp_inv, b);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+        FusedOps none;
+        GD_TRY(fft_pow2(*this, b, pl.la, pl.bhat, pl.la, pl.log2la, 1, none, st));   // FFT(b), fft/fft.go:61
+        it = blue.emplace(n, pl).first;
+    }
+    *out = &it->second;
+    return GD_OK;
+}
+
+static Status bluestein_fft(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, long long n,
+                            long long batch, bool real_in, int dir, cudaStream_t st) {
+    const BluesteinPlan* pl;
+    GD_TRY(d.bluestein(n, st, &pl));
+    const long long la = pl->la;
+    long long chunk = (long long)((64ull << 20) / ((size_t)la * sizeof(cpx)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    cpx* A;
+    GD_TRY(d.ensure_scratch(SCR_A, (size_t)chunk * la * sizeof(cpx), (void**)&A));
+    const bool inv = dir < 0;
+    for (long long b0 = 0; b0 < batch; b0 += chunk) {
+        long long nb = batch - b0 < chunk ? batch - b0 : chunk;
+        const void* src = real_in ? (const void*)((const double*)in + b0 * in_dist) : (const void*)((const cpx*)in + b0 * in_dist);
+        // a = x * conj(chirp), zero-padded to la; A = FFT(a) * FFT(b)   (bluestein.go:70-76, fft.go:60-66)
+        // inverse: the reference transforms the index-reversed input and divides by N (fft.go:39-50); the
+        // chirp table is only accurate to ~N*eps rad, so the reversal is reproduced literally, not by conjugation
+        FusedOps f1;
+        f1.ld_flags = LD_PAD | LD_MULAUX | (real_in ? LD_REAL : 0) | (inv ? LD_REVERSE : 0);
+        f1.aux_in = pl->chirp_inv; f1.n_valid_in = n;
+        f1.st_flags = ST_MULAUX; f1.aux_out = pl->bhat;
+        GD_TRY(fft_pow2(d, src, in_dist, A, la, pl->log2la, nb, f1, st));
+        // r = IFFT(A) (swap . FFT . swap, / la); r[k] * conj(chirp)[k], k < N   (fft.go:35-52, bluestein.go:89-93)
+        FusedOps f2;
+        f2.ld_flags = LD_SWAP;
+        f2.st_flags = ST_SWAP | ST_SCALE | ST_MULAUX | ST_TRUNC | (inv ? ST_DIV : 0);
+        f2.scale = 1.0 / (double)la; f2.div = (double)n;
+        f2.aux_out = pl->chirp_inv; f2.n_valid_out = n;
+        GD_TRY(fft_pow2(d, A, la, out + b0 * out_dist, out_dist, pl->log2la, nb, f2, st));
+    }
+    return GD_OK;
+}
+
+Status fft1d(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, long long n,
+             long long batch, bool real_in, int dir, cudaStream_t st) {
+    if (n < 1 || batch < 1) return invalid("fft1d: bad size");
+    if (n == 1) {                                          // fft/fft.go:76-80 (IFFT: x/1)
+        copy1_kernel<<<grid_for(batch, 256), 256, 0, st>>>(in, in_dist, out, out_dist, batch, real_in ? 1 : 0);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+        return GD_OK;
+    }
+    if (is_pow2(n)) {
+        FusedOps ops;
+        ops.ld_flags = real_in ? LD_REAL : 0;
+        if (dir < 0) {
+            ops.ld_flags |= LD_SWAP;
+            ops.st_flags = ST_SWAP | ST_SCALE;
+            ops.scale = 1.0 / (double)n;                   // exact for power-of-two n: same bits as x / N
+        }
+        return fft_pow2(d, in, in_dist, out, out_dist, ilog2ll(n), batch, ops, st);
+    }
+    return bluestein_fft(d, in, in_dist, out, out_dist, n, batch, real_in, dir, st);
+}
+
+Status convolve(Device& d, const cpx* x, const cpx* y, cpx* out, long long n, cudaStream_t st) {
+    if (n < 1) return invalid("convolve: bad size");
+    cpx *X, *Y;
+    GD_TRY(d.ensure_scratch(SCR_B, (size_t)n * sizeof(cpx), (void**)&X));
+    GD_TRY(d.ensure_scratch(SCR_C, (size_t)n * sizeof(cpx), (void**)&Y));
+    GD_TRY(fft1d(d, x, n, X, n, n, 1, false, +1, st));
+    GD_TRY(fft1d(d, y, n, Y, n, n, 1, false, +1, st));
+    pointwise_mul_kernel<<<grid_for(n, 256), 256, 0, st>>>(X, Y, n);
+    g_launches++;
+    GD_CUDA(cudaGetLastError());
+    return fft1d(d, X, n, out, n, n, 1, false, -1, st);
+}
+
+// ------------------------------------------------------------------ N-d transforms
+// one axis: lines (o, i), o < outer, i < s, element stride s, length len. src may equal dst.
+static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir,
+                       cudaStream_t st) {
+    const long long nlines = outer * s;
+    if (len == 1) {
+        if (src != dst) GD_CUDA(cudaMemcpyAsync(dst, src, (size_t)nlines * sizeof(cpx), cudaMemcpyDeviceToDevice, st));
+        return GD_OK;
+    }
+    if (s == 1) return fft1d(d, src, len, dst, len, len, outer, false, dir, st);
+    const bool p2 = is_pow2(len);
+    if (p2 && len <= 4096) {
+        int l = ilog2ll(len);
+        PassParams p = base_params(d, l);
+        p.in = src; p.out = dst; p.nlines = nlines; p.inner = s;
+        p.in_qs = p.out_qs = len * s; p.in_is = p.out_is = 1; p.in_es = p.out_es = s;
+        p.in_mode = p.out_mode = MODE_COL;
+        if (dir < 0) { p.ld_flags = LD_SWAP; p.st_flags = ST_SWAP | ST_SCALE; p.scale = 1.0 / (double)len; }
+        return launch_pass(d, l, p, st);
+    }
+    if (p2 && len <= (1LL << 24)) {
+        // strided four-step on blocks of cb adjacent columns; the inter-pass block [len][cb] stays in L2
+        const int lg = ilog2ll(len), l1 = (lg + 1) / 2, l2 = lg - l1;
+        const long long R1 = 1LL << l1, R2 = 1LL << l2;
+        TwiddleTable tw;
+        GD_TRY(d.twiddles(lg, &tw));
+        long long cb = (long long)(d.pass_scratch_budget / ((size_t)len * sizeof(cpx)));
+        if (cb < 8) cb = 8;
+        if (cb > s) cb = s;
+        cpx* scr;
+        GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)len * cb * sizeof(cpx), (void**)&scr));
+        for (long long o = 0; o < outer; o++)
+            for (long long c0 = 0; c0 < s; c0 += cb) {
+                long long nc = s - c0 < cb ? s - c0 : cb;
+                const cpx* sp = src + o * len * s + c0;
+                cpx* dp = dst + o * len * s + c0;
+                // pass 1: lines (n2, c): length R1 over n1 (stride R2*s); out block[(k1*R2 + n2)][c]
+                PassParams p = base_params(d, l1);
+                p.in = sp; p.out = scr; p.nlines = R2 * nc; p.inner = nc;
+                p.in_qs = s; p.in_is = 1; p.in_es = R2 * s;
+                p.out_qs = nc; p.out_is = 1; p.out_es = R2 * nc;
+                p.in_mode = p.out_mode = MODE_COL;
+                if (dir < 0) p.ld_flags = LD_SWAP;
+                p.st_flags = ST_TWIDDLE; p.tw_sel = 1; p.tw_log2m = lg; p.tw_lo = tw.lo; p.tw_hi = tw.hi;
+                GD_TRY(launch_pass(d, l1, p, st));
+                // pass 2: lines (k1, c): length R2 over n2; out row (k1 + R1*k2)
+                PassParams r = base_params(d, l2);
+                r.in = scr; r.out = dp; r.nlines = R1 * nc; r.inner = nc;
+                r.in_qs = R2 * nc; r.in_is = 1; r.in_es = nc;
+                r.out_qs = s; r.out_is = 1; r.out_es = R1 * s;
+                r.in_mode = r.out_mode = MODE_COL;
+                if (dir < 0) { r.st_flags = ST_SWAP | ST_SCALE; r.scale = 1.0 / (double)len; }
+                GD_TRY(launch_pass(d, l2, r, st));
+            }
+        return GD_OK;
+    }
+    // any other length (Bluestein lines): gather to dense lines, transform, scatter back
+    long long chunk = (long long)((64ull << 20) / ((size_t)len * sizeof(cpx)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > nlines) chunk = nlines;
+    cpx* buf;
+    GD_TRY(d.ensure_scratch(SCR_B, (size_t)chunk * len * sizeof(cpx), (void**)&buf));
+    for (long long l0 = 0; l0 < nlines; l0 += chunk) {
+        long long nl = nlines - l0 < chunk ? nlines - l0 : chunk;
+        gather_lines_kernel<<<grid_for(nl * len, 256), 256, 0, st>>>(src, buf, l0, nl, len, s);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+        GD_TRY(fft1d(d, buf, len, buf, len, len, nl, false, dir, st));
+        scatter_lines_kernel<<<grid_for(nl * len, 256), 256, 0, st>>>(buf, dst, l0, nl, len, s);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+    }
+    return GD_OK;
+}
+
+Status fftn(Device& d, const cpx* in, cpx* out, const long long* dims, int nd, int dir, cudaStream_t st) {
+    if (nd < 1 || nd > 16) return invalid("fftn: bad rank");
+    long long total = 1;
+    for (int i = 0; i < nd; i++) { if (dims[i] < 1) return invalid("fftn: invalid dimensions"); total *= dims[i]; }
+    // the reference sweeps axis 0 first (fft/fft.go:175-189); FFT2 does columns (axis 0) then rows (fft.go:138-151)
+    const cpx* src = in;
+    long long outer = 1;
+    for (int a = 0; a < nd; a++) {
+        long long s = total / (outer * dims[a]);
+        GD_TRY(fft_axis(d, src, out, outer, dims[a], s, dir, st));
+        src = out;
+        outer *= dims[a];
+    }
+    return GD_OK;
+}
+
+}  // namespace gd

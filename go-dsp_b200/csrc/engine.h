@@ -1,0 +1,114 @@
+// engine.h -- device-side planner / executor behind the C ABI (include/godsp_b200.h).
+// Everything here works on DEVICE pointers and is asynchronous on the given stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fft_pass.cuh"
+
+namespace gd {
+
+enum Status : int {
+    GD_OK = 0,
+    GD_ERR_INVALID = -1,    // bad argument
+    GD_ERR_CUDA = -2,       // CUDA runtime failure (message in gd_last_error)
+    GD_ERR_NOMEM = -3,      // device / pinned allocation failed
+    GD_ERR_UNSUPPORTED = -4,
+    GD_ERR_NOT_INIT = -5,
+};
+
+extern std::atomic<long long> g_launches;   // kernels launched by this library
+
+void set_error(const std::string& msg);
+const char* last_error();
+Status cuda_fail(cudaError_t e, const char* what);
+
+#define GD_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return ::gd::cuda_fail(e__, #call); \
+    } while (0)
+#define GD_TRY(call)                          \
+    do {                                      \
+        ::gd::Status s__ = (call);            \
+        if (s__ != ::gd::GD_OK) return s__;   \
+    } while (0)
+
+// first-pass load / last-pass store hooks of a (possibly multi-pass) power-of-two transform
+struct FusedOps {
+    int ld_flags = 0;
+    const cpx* aux_in = nullptr;
+    long long n_valid_in = 0;
+    int st_flags = 0;
+    const cpx* aux_out = nullptr;
+    long long n_valid_out = 0;
+    double scale = 1.0;
+    double div = 1.0;
+};
+
+struct TwiddleTable {       // w_M^e two-level table
+    cpx* lo = nullptr;
+    cpx* hi = nullptr;
+};
+
+struct BluesteinPlan {      // fft/bluestein.go:26-65 cache, plus the cached FFT(b) (bluestein.go:78-87)
+    long long n = 0, la = 0;
+    int log2la = 0;
+    cpx* chirp_inv = nullptr;   // conj chirp, n entries
+    cpx* bhat = nullptr;        // FFT_la(b), la entries
+};
+
+enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OUT, SCR_PWELCH, SCR_AUX, SCR_NSLOTS };
+
+struct Device {
+    int dev = -1;
+    int num_sms = 0;
+    bool ready = false;
+    cudaStream_t stream = nullptr;       // compute stream of the host-pointer entry points
+    cudaStream_t stream_in = nullptr;    // H2D
+    cudaStream_t stream_out = nullptr;   // D2H
+    cpx* wl[13] = {nullptr};             // intra-line tables exp(-2 pi i e/L), L = 2^k
+    std::map<int, TwiddleTable> tw;      // keyed by log2 M
+    std::map<long long, BluesteinPlan> blue;
+    void* scratch[SCR_NSLOTS] = {nullptr};
+    size_t scratch_bytes[SCR_NSLOTS] = {0};
+    size_t pass_scratch_budget = 48ull << 20;   // inter-pass scratch kept small enough to stay L2-resident
+    bool wide_tiles = false;             // 512-thread tiles for L >= 1024
+    std::recursive_mutex mu;             // every public entry point locks its device
+
+    Status init(int device);
+    void destroy();
+    Status ensure_scratch(ScratchSlot s, size_t bytes, void** out);
+    Status twiddles(int log2m, TwiddleTable* out);
+    Status bluestein(long long n, cudaStream_t st, const BluesteinPlan** out);
+};
+
+// ---- transforms (device pointers) ----------------------------------------------------------
+// batched power-of-two transform, forward butterflies only; direction is expressed through ops
+Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, int log2n,
+                long long batch, const FusedOps& ops, cudaStream_t st);
+// fft.FFT / fft.IFFT semantics for any n >= 1 (fft/fft.go:35-52,72-87); real_in: input is float64
+Status fft1d(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, long long n,
+             long long batch, bool real_in, int dir, cudaStream_t st);
+// fft.Convolve (fft/fft.go:55-69)
+Status convolve(Device& d, const cpx* x, const cpx* y, cpx* out, long long n, cudaStream_t st);
+// fft.FFTN / IFFTN on a contiguous row-major array (fft/fft.go:166-224, dsputils/matrix.go:37-57);
+// nd == 2 is fft.FFT2 / IFFT2 (fft/fft.go:123-154). in may equal out.
+Status fftn(Device& d, const cpx* in, cpx* out, const long long* dims, int nd, int dir, cudaStream_t st);
+
+// ---- Welch PSD -----------------------------------------------------------------------------
+// raw[k] (+)= sum over local segments of |FFT(w * seg)[k]|^2 folded to k < lp; segments seg0..seg0+nseg-1
+Status pwelch_partial(Device& d, const double* x, long long nfft, long long stride, long long fftlen,
+                      long long lp, long long seg0, long long nseg, const double* win, double* raw,
+                      cudaStream_t st);
+// pxx[j] = raw[j] / nsegs (x2 for 0<j<lp-1) / norm      (spectral/pwelch.go:113-121,134-136)
+Status pwelch_finalize(const double* raw, long long lp, long long nsegs, double norm, double* pxx, cudaStream_t st);
+
+// ---- utilities -----------------------------------------------------------------------------
+Status fill_splitmix(double* out, long long n, unsigned long long seed, unsigned long long offset, cudaStream_t st);
+
+}  // namespace gd

@@ -1,0 +1,122 @@
+/*
+ * godsp_b200.h -- C ABI of libgodsp_b200.so, the B200 (sm_100a) engine behind go-dsp's
+ * exported Go API for the FFT / Welch-PSD path.
+ *
+ * The reference (github.com/mjibson/go-dsp) is pure Go with no FFI; these are the entry
+ * points a cgo shim inside its fft/ and spectral/ packages binds (INTEGRATION.md shows the
+ * shim). Each function names the reference interface it replaces (file:line relative to the
+ * go-dsp repository root).
+ *
+ * Conventions
+ *   - complex128 slices are passed as `double*` to interleaved (re, im) pairs -- the memory
+ *     layout of Go's []complex128 and of CUDA's double2; []float64 as `double*`.
+ *   - every function returns 0 on success or a negative gd_status; gd_last_error() gives the
+ *     message (thread-local). There is NO CPU fallback: without a B200 every compute entry
+ *     point fails with GD_ERR_CUDA / GD_ERR_UNSUPPORTED and the Go shim panics.
+ *   - host-pointer entry points are synchronous: the caller owns all buffers, `out` must not
+ *     alias `in`, nothing is retained after return (cgo pointer rules). Pageable and pinned
+ *     (gd_pinned_alloc) host memory are both accepted; pinned memory is copied asynchronously.
+ *   - entry points may be called from any OS thread (goroutines migrate): each call selects
+ *     its CUDA device explicitly and serialises on that device's mutex.
+ *   - dir: +1 forward (fft.FFT), -1 inverse including the 1/N (fft.IFFT).
+ */
+#ifndef GODSP_B200_H
+#define GODSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GD_API __attribute__((visibility("default")))
+#else
+#define GD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum gd_status {
+    GD_OK = 0,
+    GD_ERR_INVALID = -1,      /* bad argument (the Go shim checks and panics with the reference's strings first) */
+    GD_ERR_CUDA = -2,         /* CUDA runtime failure */
+    GD_ERR_NOMEM = -3,        /* device or pinned allocation failed */
+    GD_ERR_UNSUPPORTED = -4,  /* size outside what this build plans (e.g. one transform > 2^24 points on one GPU) */
+    GD_ERR_NOT_INIT = -5
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* Initialise devices 0..ndev-1 (ndev <= 0: every visible device). Idempotent. Called lazily
+ * (with ndev = 1) by every other entry point, so a Go program never has to call it. */
+GD_API int gd_init(int ndev);
+GD_API int gd_shutdown(void);
+GD_API const char* gd_last_error(void);
+GD_API int gd_device_count(void);            /* initialised devices */
+GD_API int gd_use_device(int dev);           /* device used by subsequent calls from this thread (default 0) */
+/* Tuning knobs: "pass_scratch_mb" (inter-pass scratch kept L2-resident), "wide_tiles" (0/1). */
+GD_API int gd_set_option(const char* key, int64_t value);
+
+/* ---- fft package ----------------------------------------------------------------------- */
+/* fft.FFT (fft/fft.go:72-87) / fft.IFFT (fft/fft.go:35-52): any n >= 1; power-of-two n runs the
+ * Stockham passes that replace radix2FFT (fft/radix2.go:80-154), other n the fused Bluestein path
+ * that replaces bluesteinFFT (fft/bluestein.go:68-94). */
+GD_API int gd_fft_c2c(const double* in, double* out, int64_t n, int dir);
+/* fft.FFTReal / fft.IFFTReal (fft/fft.go:25-32): float64 in, full n-bin complex out; the
+ * dsputils.ToComplex widening (dsputils/dsputils.go:25-31) is fused into the first load. */
+GD_API int gd_fft_r2c_full(const double* in_real, double* out, int64_t n, int dir);
+/* `batch` independent transforms stored back to back (additive API: the reference has no batch
+ * call; this is what a loop of fft.FFT over rows lowers to). */
+GD_API int gd_fft_batch_c2c(const double* in, double* out, int64_t n, int64_t batch, int dir);
+/* fft.Convolve (fft/fft.go:55-69), equal lengths (the shim panics "arrays not of equal size"). */
+GD_API int gd_convolve_c2c(const double* x, const double* y, double* out, int64_t n);
+/* fft.FFT2 / fft.IFFT2 (fft/fft.go:109-154) on a dense row-major rows x cols array (the shim
+ * stages [][]complex128 rows into one pinned block). */
+GD_API int gd_fft2_c2c(const double* in, double* out, int64_t rows, int64_t cols, int dir);
+/* fft.FFTN / fft.IFFTN (fft/fft.go:157-224) on dsputils.Matrix's flat row-major list
+ * (dsputils/matrix.go:21-57: last dimension fastest). */
+GD_API int gd_fftn_c2c(const double* in, double* out, const int64_t* dims, int nd, int dir);
+/* fft.EnsureRadix2Factors (fft/radix2.go:35-37): build and cache the tables / Bluestein plan for n. */
+GD_API int gd_plan_warm(int64_t n);
+/* dsputils.NextPowerOf2(2n-1) (dsputils/dsputils.go:39-45) as the engine computes it: the
+ * Bluestein padded length for n (bit-exact requirement). */
+GD_API int64_t gd_bluestein_padded_len(int64_t n);
+
+/* ---- spectral package ------------------------------------------------------------------ */
+/* The segment loop of spectral.Pwelch (spectral/pwelch.go:104-122,134-136). The Go side keeps
+ * the option defaults, window evaluation, norm and freqs (pwelch.go:85-102,124-132,138-142):
+ *   nfft, noverlap : resolved option values;  fftlen = max(pad, nfft);  lp = pad/2 + 1
+ *   nsegs          : len(spectral.Segment(x, nfft, noverlap)) (spectral/spectral.go:22-33)
+ *   win            : Window(fftlen) (window.Apply, window/window.go:25-29)
+ *   norm           : sum(Window(nfft)^2) [* Fs]
+ * x must hold at least (nsegs-1)*(nfft-noverlap) + nfft samples. pxx receives lp values. */
+GD_API int gd_pwelch_f64(const double* x, int64_t nx, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
+                  int64_t nsegs, const double* win, double norm, double* pxx);
+
+/* ---- staging memory for the shim -------------------------------------------------------- */
+GD_API void* gd_pinned_alloc(size_t bytes);
+GD_API void gd_pinned_free(void* p);
+
+/* ---- device-resident API (benchmarks, verification, the additive batched Go API) -------- */
+/* Device pointers; asynchronous on `stream` (a cudaStream_t; NULL = the library's stream). */
+GD_API int gd_dev_alloc(void** p, size_t bytes);
+GD_API int gd_dev_free(void* p);
+GD_API int gd_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
+GD_API int gd_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
+GD_API int gd_stream_sync(void* stream);
+GD_API int gd_fill_splitmix_dev(double* dst_dev, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+GD_API int gd_fft_batch_c2c_dev(const double* in_dev, double* out_dev, int64_t n, int64_t batch, int dir, void* stream);
+GD_API int gd_fft_batch_r2c_full_dev(const double* in_dev, double* out_dev, int64_t n, int64_t batch, int dir, void* stream);
+GD_API int gd_convolve_c2c_dev(const double* x_dev, const double* y_dev, double* out_dev, int64_t n, void* stream);
+GD_API int gd_fftn_c2c_dev(const double* in_dev, double* out_dev, const int64_t* dims, int nd, int dir, void* stream);
+/* raw[j] = sum over segments seg0..seg0+nseg-1 of |FFT(win * segment)[j]|^2, j < lp (one GPU's share) */
+GD_API int gd_pwelch_partial_dev(const double* x_dev, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
+                          int64_t seg0, int64_t nseg, const double* win_dev, double* raw_dev, void* stream);
+/* pxx[j] = raw[j] / nsegs (x2 for 0 < j < lp-1) / norm */
+GD_API int gd_pwelch_finalize_dev(const double* raw_dev, int64_t lp, int64_t nsegs, double norm, double* pxx_dev, void* stream);
+/* number of kernels this library has launched on the calling thread's device since gd_init */
+GD_API int64_t gd_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GODSP_B200_H */
