@@ -1,0 +1,425 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the go-dsp hot path on B200: batched 2^20-point complex128 FFT
+(GS/s, the headline) and spectral.Pwelch (Msamples/s, reported in the same JSON line).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (C ABI)
+    python bench.py --impl reference --gpus N ...            # go-dsp's CPU algorithm (oracle port) on host cores
+
+One process per GPU (torchrun for N > 1, one rank per GPU); batches / segment ranges are
+sharded across ranks with no data-path collective (Pwelch adds one 2049-double all-gather).
+A "step" is one pass of the hot path over one batch of synthetic input (SplitMix64 counter
+generator). Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks. Inputs are far larger than the 126 MB L2.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "go-dsp_b200"))
+
+LOG2N = 20
+FFT_SEED, PW_SEED = 3, 5
+PW_NFFT, PW_NOVERLAP = 4096, 2048
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="2^20-point transforms per GPU per step")
+    ap.add_argument("--pw-log2-samples", type=int, default=30, help="Pwelch samples per GPU per step (log2)")
+    ap.add_argument("--e2e-batch", type=int, default=256, help="transforms per GPU in the host-buffer (e2e) run")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--skip", default="", help="comma list: pwelch,e2e,cpu")
+    ap.add_argument("--scratch-mb", type=int, default=0, help="override the inter-pass scratch budget")
+    ap.add_argument("--wide-tiles", type=int, default=-1)
+    ap.add_argument("--fused", type=int, default=-1)
+    ap.add_argument("--fused-slot-mb", type=int, default=0)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- helpers
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = index, [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.ok:
+            self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+# --------------------------------------------------------------------------- reference arm (CPU)
+def cpu_fft_sample(threads, budget_s):
+    """oracle port of fft.FFT (fft/radix2.go) on `threads` host threads; returns (GS/s, description)."""
+    import oracle
+    n = 1 << LOG2N
+    x1 = oracle.splitmix_complex(n, FFT_SEED)
+    oracle.fft(x1)                                   # builds the twiddle tables (EnsureRadix2Factors)
+    t0 = time.perf_counter()
+    oracle.fft(x1)
+    t1 = time.perf_counter() - t0
+    batch = int(max(threads, min(16 * threads, budget_s * threads / max(t1, 1e-3))))
+    xs = np.empty((batch, n), np.complex128)
+    for b in range(batch):
+        xs[b] = oracle.splitmix_complex(n, FFT_SEED, b << 21) if b < 4 else xs[b % 4]
+    t0 = time.perf_counter()
+    oracle.fft_batch(xs, threads=threads)
+    dt = time.perf_counter() - t0
+    return batch * n / dt / 1e9, "%d transforms of 2^20 points, one transform per thread at a time" % batch, dt
+
+
+def cpu_pwelch_sample(threads, budget_s):
+    import oracle
+    log2s = 24
+    x = oracle.fill_splitmix(1 << log2s, PW_SEED)
+    t0 = time.perf_counter()
+    oracle.pwelch(x, 1.0, nfft=PW_NFFT, noverlap=PW_NOVERLAP, threads=threads)
+    dt = time.perf_counter() - t0
+    reps = int(max(1, min(8, budget_s / max(dt, 1e-3))))
+    if reps > 1:
+        x = np.tile(x, reps)
+        t0 = time.perf_counter()
+        oracle.pwelch(x, 1.0, nfft=PW_NFFT, noverlap=PW_NOVERLAP, threads=threads)
+        dt = time.perf_counter() - t0
+    return x.shape[0] / dt / 1e6, "%d samples, NFFT 4096, Noverlap 2048, Hann; segment ranges split over threads" % x.shape[0], dt
+
+
+def run_reference(args):
+    world, rank, _ = dist_setup(args)
+    if rank != 0:
+        return
+    import oracle
+    threads = os.cpu_count() or 1
+    per_step = max(2.0, min(10.0, 150.0 / max(1, args.steps + args.warmup) / 2))
+    vals, pvals, times, desc, pdesc = [], [], [], "", ""
+    for i in range(args.warmup + args.steps):
+        v, desc, dt = cpu_fft_sample(threads, per_step)
+        pv, pdesc, _ = cpu_pwelch_sample(threads, per_step)
+        if i >= args.warmup:
+            vals.append(v)
+            pvals.append(pv)
+            times.append(dt)
+    v = float(np.mean(vals))
+    pv = float(np.mean(pvals))
+    n = 1 << LOG2N
+    line = {
+        "impl": "reference", "metric": "FFT GS/s (complex128, 2^20-pt batched)", "value": v, "unit": "GS/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+        "config": {"workload": "batched 2^20-point complex128 FFT (BASELINE.json configs[2]); CPU arm times a bounded sample per step",
+                   "n": n, "sample": desc},
+        "cpu_baseline": {"value": v, "unit": "GS/s", "cores": threads, "kind": "port",
+                         "sample": desc + "; C restatement of go-dsp (oracle/godsp_oracle.c), not the Go binary (no Go toolchain)"},
+        "e2e": {"value": v, "unit": "GS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pwelch": {"metric": "Pwelch Msamples/s", "value": pv, "unit": "Msamples/s",
+                   "cpu_baseline": {"value": pv, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": pdesc},
+                   "e2e": {"value": pv, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm (GPU)
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from godsp import _capi as capi
+
+    world, rank, local = dist_setup(args)
+    skip = set(s for s in args.skip.split(",") if s)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; go-dsp_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = capi.lib()
+    capi.check(L.gd_use_device(local))
+    if args.scratch_mb > 0:
+        capi.check(L.gd_set_option(b"pass_scratch_mb", args.scratch_mb))
+    if args.wide_tiles >= 0:
+        capi.check(L.gd_set_option(b"wide_tiles", args.wide_tiles))
+    if args.fused >= 0:
+        capi.check(L.gd_set_option(b"fused", args.fused))
+    if args.fused_slot_mb > 0:
+        capi.check(L.gd_set_option(b"fused_slot_mb", args.fused_slot_mb))
+    # a dedicated (non-default) stream: the events below and every kernel of the library share it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """returns (ms per step, max over ranks), launches in the timed region, clocks"""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = L.gd_kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = L.gd_kernel_launches() - l0
+        clocks = sampler.result()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, launches, clocks
+
+    def timed_host(fn, steps, warmup):
+        """wall clock around synchronous host-buffer calls (copies inside), max over ranks"""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    n = 1 << LOG2N
+    # ---------------- FFT: device-resident
+    free_b, _ = torch.cuda.mem_get_info()
+    batch = args.batch
+    max_batch = int((free_b - (6 << 30)) // (2 * n * 16))
+    if batch > max_batch:
+        batch = max(1, max_batch)
+    x = torch.empty(batch * n * 2, dtype=torch.float64, device="cuda")
+    y = torch.empty(batch * n * 2, dtype=torch.float64, device="cuda")
+    row0 = rank * batch                 # global batch row of this rank's first transform
+    capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), batch * n * 2, FFT_SEED, (row0 << 21) * 2, sp))
+    torch.cuda.synchronize()
+
+    def fft_step():
+        capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, batch, 1, sp))
+
+    ms, launches, clocks = timed(fft_step, args.steps, args.warmup)
+    pts = batch * n * world
+    value = pts / (ms * 1e-3) / 1e9
+    per_gpu_bytes = 32.0 * batch * n
+    achieved = per_gpu_bytes / (ms * 1e-3) / 1e9
+    launches_per_step = launches / max(1, args.steps)
+    line = {
+        "metric": "FFT GS/s (complex128, 2^20-pt batched)", "value": value, "unit": "GS/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+        "config": {"workload": "batched 2^20-point complex128 FFT (BASELINE.json configs[2]), %d transforms per GPU per step" % batch,
+                   "n": n, "batch_per_gpu": batch, "global_batch": batch * world, "direction": "forward",
+                   "residency": "inputs and outputs resident in HBM (generated on device, SplitMix64 seed 3)",
+                   "l2": "inputs (%.1f GiB per GPU) are far larger than L2; no flush needed" % (batch * n * 16 / 2**30),
+                   "parallelism": "batch rows sharded over %d GPU(s), no collective" % world},
+        "roofline": {"bound": "hbm", "kernel": "gd::fft_pass_kernel<10,4,false> (both four-step passes are launches of this kernel)",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": per_gpu_bytes / max(1.0, launches_per_step),
+                     "avg_launch_us": ms * 1e3 / max(1.0, launches_per_step),
+                     "note": "32 B/point (16 read + 16 written once, SURVEY.md 8d) x points per step / CUDA-event step time; each launch is one pass over one chunk and is charged half"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+    # ---------------- FFT: end to end through the host-buffer C ABI
+    if "e2e" not in skip:
+        eb = min(args.e2e_batch, batch)
+        nbytes = eb * n * 16
+        L.gd_pinned_alloc.restype = C.c_void_p
+        hin, hout = L.gd_pinned_alloc(nbytes), L.gd_pinned_alloc(nbytes)
+        if not hin or not hout:
+            raise SystemExit("pinned allocation failed: " + L.gd_last_error().decode())
+        hin_np = np.ctypeslib.as_array((C.c_double * (eb * n * 2)).from_address(hin))
+        capi.check(L.gd_memcpy_d2h(hin, x.data_ptr(), nbytes))        # same synthetic rows, now in pinned host memory
+
+        def e2e_step():
+            capi.check(L.gd_fft_batch_c2c(hin, hout, n, eb, 1))
+
+        ems = timed_host(e2e_step, args.e2e_steps, 1)
+        line["e2e"] = {"value": eb * n * world / (ems * 1e-3) / 1e9, "unit": "GS/s", "h2d_bytes_per_step": nbytes,
+                       "d2h_bytes_per_step": nbytes, "ms_per_step": ems, "batch_per_gpu": eb,
+                       "api": "gd_fft_batch_c2c (pinned host in/out; chunked H2D / kernels / D2H overlap on 3 streams)"}
+        # spot check: e2e output equals the device-resident output for the same rows
+        hout_np = np.ctypeslib.as_array((C.c_double * (eb * n * 2)).from_address(hout))
+        ref = y[: 2 * n].cpu().numpy()
+        line["e2e"]["matches_device_path"] = bool(np.array_equal(hout_np[: 2 * n], ref))
+        del hin_np, hout_np
+        L.gd_pinned_free(hin)
+        L.gd_pinned_free(hout)
+
+    # ---------------- FFT: CPU baseline (rank 0, N = 1 only)
+    if "cpu" not in skip and world == 1:
+        threads = os.cpu_count() or 1
+        v, desc, _ = cpu_fft_sample(threads, 1.5)
+        line["cpu_baseline"] = {"value": v, "unit": "GS/s", "cores": threads, "kind": "port",
+                                "sample": desc + "; C restatement of go-dsp (oracle/godsp_oracle.c), not the Go binary"}
+    del x, y
+    torch.cuda.empty_cache()
+
+    # ---------------- Pwelch
+    if "pwelch" not in skip:
+        line["pwelch"] = run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_host, skip, hbm_peak, peak_src)
+        line["gpu_launches"] += line["pwelch"].pop("_launches")
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_host, skip, hbm_peak, peak_src):
+    import oracle  # window table + norm only (host-side O(NFFT) work the Go shim does); not on the timed path
+    nfft, nov = PW_NFFT, PW_NOVERLAP
+    stride = nfft - nov
+    ns_local = 1 << args.pw_log2_samples                   # samples owned by this rank
+    total = ns_local * world
+    nsegs = (total - nfft) // stride + 1                   # spectral.Segment count (spectral/spectral.go:22-33)
+    lp = nfft // 2 + 1
+    # rank r owns segments [s0, s1): those starting inside its sample range
+    s0 = rank * ns_local // stride
+    s1 = min(nsegs, (rank + 1) * ns_local // stride)
+    halo = nov if rank < world - 1 else 0
+    nloc = ns_local + halo
+    x = torch.empty(nloc, dtype=torch.float64, device="cuda")
+    capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), nloc, PW_SEED, rank * ns_local, sp))
+    win = oracle.window("hann", nfft)
+    norm = 0.0
+    for v in win:
+        norm += v * v                                       # spectral/pwelch.go:124-128 (Fs = 1)
+    dwin = torch.from_numpy(win).cuda()
+    raw = torch.empty(lp, dtype=torch.float64, device="cuda")
+    pxx = torch.empty(lp, dtype=torch.float64, device="cuda")
+    gathered = [torch.empty(lp, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def step():
+        capi.check(L.gd_pwelch_partial_dev(x.data_ptr(), nfft, nov, nfft, lp, 0, s1 - s0, dwin.data_ptr(), raw.data_ptr(), sp))
+        if world > 1:
+            dist.all_gather(gathered, raw)
+            tot = gathered[0].clone()
+            for g in gathered[1:]:
+                tot += g                                    # fixed rank order: reproducible
+            capi.check(L.gd_pwelch_finalize_dev(tot.data_ptr(), lp, nsegs, norm, pxx.data_ptr(), sp))
+        else:
+            capi.check(L.gd_pwelch_finalize_dev(raw.data_ptr(), lp, nsegs, norm, pxx.data_ptr(), sp))
+
+    ms, launches, clocks = timed(step, args.steps, args.warmup)
+    value = total / (ms * 1e-3) / 1e6
+    achieved = 8.0 * ns_local / (ms * 1e-3) / 1e9
+    out = {
+        "metric": "Pwelch Msamples/s", "value": value, "unit": "Msamples/s", "ms_per_step": ms, "scaling": "weak",
+        "config": {"workload": "spectral.Pwelch, %d float64 samples per GPU, NFFT 4096, Noverlap 2048, Hann (BASELINE.json configs[3])" % ns_local,
+                   "samples_per_gpu": ns_local, "segments_total": int(nsegs), "bins": lp,
+                   "parallelism": "segment ranges sharded over %d GPU(s); one %d-double all-gather, summed in rank order" % (world, lp)},
+        "roofline": {"bound": "hbm", "kernel": "gd::pwelch_fused_kernel<12>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": None,
+                     "note": "8 B per input sample (SURVEY.md 8d); FP64 issue rate, not HBM, is the tighter roof for this kernel (DESIGN.md)"},
+        "clocks": clocks, "_launches": int(launches),
+        "pxx_checksum": float(pxx.sum().item()),
+    }
+    if "e2e" not in skip:
+        nbytes = nloc * 8
+        L.gd_pinned_alloc.restype = C.c_void_p
+        hx = L.gd_pinned_alloc(nbytes)
+        if not hx:
+            raise SystemExit("pinned allocation failed: " + L.gd_last_error().decode())
+        capi.check(L.gd_memcpy_d2h(hx, x.data_ptr(), nbytes))
+        hp = np.empty(lp)
+        nseg_loc = s1 - s0
+
+        def e2e_step():
+            capi.check(L.gd_pwelch_f64(hx, nloc, nfft, nov, nfft, lp, nseg_loc, win.ctypes.data, norm, hp.ctypes.data))
+
+        ems = timed_host(e2e_step, args.e2e_steps, 1)
+        out["e2e"] = {"value": total / (ems * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": nbytes,
+                      "d2h_bytes_per_step": lp * 8, "ms_per_step": ems,
+                      "api": "gd_pwelch_f64 (pinned host signal streamed in 256 MiB ranges, H2D overlapped with the fused kernel)"}
+        L.gd_pinned_free(hx)
+    if "cpu" not in skip and world == 1:
+        threads = os.cpu_count() or 1
+        v, desc, _ = cpu_pwelch_sample(threads, 1.5)
+        out["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                               "sample": desc + "; C restatement of go-dsp, not the Go binary"}
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -37,17 +37,32 @@ Status ensure_events(int dev) {
     return ::gd::GD_OK;
 }
 
+// devices are initialised one by one, on first use (a torchrun rank only ever touches its own GPU)
+Status ensure_device(int dev) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (g_ndev.load() == 0) {
+        int have = 0;
+        cudaError_t e = cudaGetDeviceCount(&have);
+        if (e != cudaSuccess || have < 1) {
+            set_error(std::string("no CUDA device: go-dsp_b200 has no CPU fallback (") +
+                      (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") + ")");
+            return ::gd::GD_ERR_CUDA;
+        }
+        g_ndev.store(have > kMaxDev ? kMaxDev : have);
+    }
+    if (dev < 0 || dev >= g_ndev.load()) { set_error("device index out of range"); return ::gd::GD_ERR_INVALID; }
+    if (!g_dev[dev].ready) GD_TRY(g_dev[dev].init(dev));
+    return ::gd::GD_OK;
+}
+
 // RAII: select + lock the calling thread's device
 struct DevLock {
     Device* d = nullptr;
     Status st = ::gd::GD_OK;
     std::unique_lock<std::recursive_mutex> lk;
     DevLock() {
-        if (g_ndev.load() == 0) {
-            int rc = gd_init(1);
-            if (rc != 0) { st = (Status)rc; return; }
-        }
-        if (t_dev < 0 || t_dev >= g_ndev.load()) { set_error("device index out of range"); st = ::gd::GD_ERR_INVALID; return; }
+        st = ensure_device(t_dev);
+        if (st != ::gd::GD_OK) return;
         d = &g_dev[t_dev];
         lk = std::unique_lock<std::recursive_mutex>(d->mu);
         cudaError_t e = cudaSetDevice(d->dev);
@@ -86,28 +101,20 @@ __global__ void add_inplace_kernel(double* tot, const double* part, long long n)
 extern "C" {
 
 int gd_init(int ndev) {
-    std::lock_guard<std::mutex> lk(g_init_mu);
-    int have = 0;
-    cudaError_t e = cudaGetDeviceCount(&have);
-    if (e != cudaSuccess || have < 1) {
-        set_error(std::string("no CUDA device: go-dsp_b200 has no CPU fallback (") +
-                  (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") + ")");
-        return ::gd::GD_ERR_CUDA;
-    }
-    if (ndev <= 0 || ndev > have) ndev = have;
-    if (ndev > kMaxDev) ndev = kMaxDev;
-    for (int i = g_ndev.load(); i < ndev; i++) {
-        Status s = g_dev[i].init(i);
+    Status s = ensure_device(0);
+    if (s != ::gd::GD_OK) return (int)s;
+    if (ndev <= 0 || ndev > g_ndev.load()) ndev = g_ndev.load();
+    for (int i = 1; i < ndev; i++) {
+        s = ensure_device(i);
         if (s != ::gd::GD_OK) return (int)s;
-        g_ndev.store(i + 1);
     }
-    cudaSetDevice(g_dev[t_dev < g_ndev.load() ? t_dev : 0].dev);
     return ::gd::GD_OK;
 }
 
 int gd_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_init_mu);
     for (int i = 0; i < g_ndev.load(); i++) {
+        if (!g_dev[i].ready) continue;
         g_dev[i].destroy();
         StageEvents& e = g_ev[i];
         if (e.ready) {
@@ -115,17 +122,20 @@ int gd_shutdown(void) {
             e.ready = false;
         }
     }
-    g_ndev.store(0);
     return ::gd::GD_OK;
 }
 
 const char* gd_last_error(void) { return last_error(); }
-int gd_device_count(void) { return g_ndev.load(); }
+
+int gd_device_count(void) {
+    int n = 0;
+    for (int i = 0; i < g_ndev.load(); i++) n += g_dev[i].ready ? 1 : 0;
+    return n;
+}
 
 int gd_use_device(int dev) {
-    if (g_ndev.load() == 0) { int rc = gd_init(dev + 1); if (rc) return rc; }
-    if (dev >= g_ndev.load()) { int rc = gd_init(dev + 1); if (rc) return rc; }
-    if (dev < 0 || dev >= g_ndev.load()) return (int)invalid_arg("gd_use_device: no such device");
+    Status s = ensure_device(dev);
+    if (s != ::gd::GD_OK) return (int)s;
     t_dev = dev;
     return ::gd::GD_OK;
 }
@@ -134,6 +144,10 @@ int gd_set_option(const char* key, int64_t value) {
     GD_ENTER();
     if (!strcmp(key, "pass_scratch_mb")) { if (value < 1) return (int)invalid_arg("pass_scratch_mb < 1"); d.pass_scratch_budget = (size_t)value << 20; }
     else if (!strcmp(key, "wide_tiles")) d.wide_tiles = value != 0;
+    else if (!strcmp(key, "fused")) d.use_fused = value != 0;
+    else if (!strcmp(key, "l2_window")) d.use_l2_window = value != 0;
+    else if (!strcmp(key, "fused_delay")) { if (value < 1 || value > 6) return (int)invalid_arg("fused_delay out of range"); d.fused_delay = (int)value; }
+    else if (!strcmp(key, "fused_slot_mb")) { if (value < 1) return (int)invalid_arg("fused_slot_mb < 1"); d.fused_slot_budget = (size_t)value << 20; }
     else return (int)invalid_arg("gd_set_option: unknown key");
     return ::gd::GD_OK;
 }
@@ -290,7 +304,7 @@ int gd_pwelch_f64(const double* x, int64_t nx, int64_t nfft, int64_t noverlap, i
 }
 
 void* gd_pinned_alloc(size_t bytes) {
-    if (g_ndev.load() == 0 && gd_init(1) != 0) return nullptr;
+    if (ensure_device(t_dev) != ::gd::GD_OK) return nullptr;
     void* p = nullptr;
     cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
     if (e != cudaSuccess) { cuda_fail(e, "cudaHostAlloc"); return nullptr; }

@@ -6,9 +6,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "fft_fused.cuh"
 #include "pass_launch.cuh"
 
 namespace gd {
+
+cudaError_t launch_fused(int log2l, const FusedParams& a, long long total_items, int num_sms, cudaStream_t st);
+int fused_tile_lines(int log2l);
 
 // ------------------------------------------------------------------ errors
 std::atomic<long long> g_launches{0};
@@ -62,6 +66,9 @@ Status Device::init(int device) {
         return GD_ERR_UNSUPPORTED;
     }
     num_sms = prop.multiProcessorCount;
+    l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (l2_persist_max) GD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max));
     GD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     GD_CUDA(cudaStreamCreateWithFlags(&stream_in, cudaStreamNonBlocking));
     GD_CUDA(cudaStreamCreateWithFlags(&stream_out, cudaStreamNonBlocking));
@@ -75,6 +82,10 @@ Status Device::init(int device) {
         if (v > 0) pass_scratch_budget = (size_t)v << 20;
     }
     if (const char* s = getenv("GD_WIDE_TILES")) wide_tiles = atoi(s) != 0;
+    if (const char* s = getenv("GD_FUSED")) use_fused = atoi(s) != 0;
+    if (const char* s = getenv("GD_L2_WINDOW")) use_l2_window = atoi(s) != 0;
+    if (const char* s = getenv("GD_FUSED_DELAY")) { int v = atoi(s); if (v >= 1 && v <= 6) fused_delay = v; }
+    if (getenv("GD_VERBOSE")) fprintf(stderr, "[godsp] dev %d: %d SMs, L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", dev, num_sms, prop.l2CacheSize >> 20, l2_persist_max >> 20, l2_window_max >> 20);
     ready = true;
     return GD_OK;
 }
@@ -170,6 +181,54 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         return launch_pass(d, log2n, p, st);
     }
     if (log2n > 24) return invalid("fft_pow2: N > 2^24 needs the multi-GPU path");
+    const bool lean = !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
+    if (d.use_fused && lean && (log2n % 2) == 0 && log2n >= 16 && batch * (2LL << (log2n / 2)) < (1LL << 30)) {
+        // both passes in one persistent kernel, intermediate resident in L2 (fft_fused.cuh)
+        const int l = log2n / 2, T = fused_tile_lines(l), tpt = (1 << l) / T;
+        TwiddleTable tw;
+        GD_TRY(d.twiddles(log2n, &tw));
+        long long J = (2LL * d.num_sms * 2 + tpt - 1) / tpt;               // ~2 rounds of resident CTAs per phase
+        long long jcap = (long long)(d.fused_slot_budget / ((size_t)N * sizeof(cpx)));
+        if (jcap < 1) jcap = 1;
+        if (J > jcap) J = jcap;
+        if (J > batch) J = batch;
+        FusedParams f;
+        memset(&f, 0, sizeof(f));
+        f.in = (const cpx*)in; f.out = out; f.in_dist = in_dist; f.out_dist = out_dist;
+        f.batch = (int)batch; f.group_tf = (int)J; f.ngroups = (int)((batch + J - 1) / J);
+        f.log2n = log2n; f.ld_conj = (ops.ld_flags & LD_CONJ) ? 1 : 0; f.st_flags = ops.st_flags; f.scale = ops.scale;
+        f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.wl = d.wl[l];
+        if (const char* dbg = getenv("GD_FUSED_DEBUG")) f.debug = atoi(dbg);
+        f.delay = d.fused_delay; f.nslots = d.fused_delay + 2;
+        GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)(d.fused_delay + 2) * J * N * sizeof(cpx), (void**)&f.scratch));
+        int* cnt;
+        GD_TRY(d.ensure_scratch(SCR_CNT, (2 * (size_t)f.ngroups + 1) * sizeof(int), (void**)&cnt));
+        GD_CUDA(cudaMemsetAsync(cnt, 0, (2 * (size_t)f.ngroups + 1) * sizeof(int), st));
+        f.done1 = cnt; f.done2 = cnt + f.ngroups; f.next_item = cnt + 2 * f.ngroups;
+        long long total_items = 2LL * f.ngroups * J * tpt;
+        // keep the scratch slots resident in L2: persisting access-policy window for this launch
+        const size_t scr_bytes = (size_t)(d.fused_delay + 2) * J * N * sizeof(cpx);
+        const bool window = d.use_l2_window && d.l2_persist_max > 0 && d.l2_window_max > 0;
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        if (window) {
+            attr.accessPolicyWindow.base_ptr = f.scratch;
+            attr.accessPolicyWindow.num_bytes = scr_bytes < d.l2_window_max ? scr_bytes : d.l2_window_max;
+            double ratio = (double)d.l2_persist_max / (double)attr.accessPolicyWindow.num_bytes;
+            attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            GD_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+        }
+        cudaError_t e = launch_fused(l, f, total_items, d.num_sms, st);
+        if (window) {
+            attr.accessPolicyWindow.num_bytes = 0;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "fft_fused_kernel launch");
+        g_launches++;
+        return GD_OK;
+    }
     // four-step: N = N1 * N2, n = n1*N2 + n2, k = k1 + N1*k2
     const int l1 = (log2n + 1) / 2, l2 = log2n - l1;
     const long long N1 = 1LL << l1, N2 = 1LL << l2;
@@ -188,8 +247,8 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         p.in = real_in ? (const void*)((const double*)in + b0 * in_dist) : (const void*)((const cpx*)in + b0 * in_dist);
         p.out = scr;
         p.nlines = nb * N2; p.inner = N2;
-        p.in_qs = in_dist; p.in_is = 1; p.in_es = N2;
-        p.out_qs = N; p.out_is = 1; p.out_es = N2;
+        p.in_qs = in_dist; p.in_is = 1; p.in_es = (int)N2;
+        p.out_qs = N; p.out_is = 1; p.out_es = (int)N2;
         p.in_mode = p.out_mode = MODE_COL;
         p.ld_flags = ops.ld_flags; p.aux_in = ops.aux_in; p.n_valid_in = ops.n_valid_in;
         p.st_flags = ST_TWIDDLE; p.tw_sel = 0; p.tw_log2m = log2n; p.tw_lo = tw.lo; p.tw_hi = tw.hi;
@@ -199,7 +258,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         r.in = scr; r.out = out + b0 * out_dist;
         r.nlines = nb * N1; r.inner = N1;
         r.in_qs = N; r.in_is = N2; r.in_es = 1;
-        r.out_qs = out_dist; r.out_is = 1; r.out_es = N1;
+        r.out_qs = out_dist; r.out_is = 1; r.out_es = (int)N1;
         r.in_mode = MODE_ROW; r.out_mode = MODE_COL;
         r.st_flags = ops.st_flags; r.aux_out = ops.aux_out; r.n_valid_out = ops.n_valid_out;
         r.scale = ops.scale; r.div = ops.div;
@@ -325,10 +384,10 @@ static Status bluestein_fft(Device& d, const void* in, long long in_dist, cpx* o
         f1.aux_in = pl->chirp_inv; f1.n_valid_in = n;
         f1.st_flags = ST_MULAUX; f1.aux_out = pl->bhat;
         GD_TRY(fft_pow2(d, src, in_dist, A, la, pl->log2la, nb, f1, st));
-        // r = IFFT(A) (swap . FFT . swap, / la); r[k] * conj(chirp)[k], k < N   (fft.go:35-52, bluestein.go:89-93)
+        // r = IFFT(A) (conj . FFT . conj, / la); r[k] * conj(chirp)[k], k < N   (fft.go:35-52, bluestein.go:89-93)
         FusedOps f2;
-        f2.ld_flags = LD_SWAP;
-        f2.st_flags = ST_SWAP | ST_SCALE | ST_MULAUX | ST_TRUNC | (inv ? ST_DIV : 0);
+        f2.ld_flags = LD_CONJ;
+        f2.st_flags = ST_CONJ | ST_SCALE | ST_MULAUX | ST_TRUNC | (inv ? ST_DIV : 0);
         f2.scale = 1.0 / (double)la; f2.div = (double)n;
         f2.aux_out = pl->chirp_inv; f2.n_valid_out = n;
         GD_TRY(fft_pow2(d, A, la, out + b0 * out_dist, out_dist, pl->log2la, nb, f2, st));
@@ -349,8 +408,8 @@ Status fft1d(Device& d, const void* in, long long in_dist, cpx* out, long long o
         FusedOps ops;
         ops.ld_flags = real_in ? LD_REAL : 0;
         if (dir < 0) {
-            ops.ld_flags |= LD_SWAP;
-            ops.st_flags = ST_SWAP | ST_SCALE;
+            ops.ld_flags |= LD_CONJ;
+            ops.st_flags = ST_CONJ | ST_SCALE;
             ops.scale = 1.0 / (double)n;                   // exact for power-of-two n: same bits as x / N
         }
         return fft_pow2(d, in, in_dist, out, out_dist, ilog2ll(n), batch, ops, st);
@@ -382,16 +441,17 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
     }
     if (s == 1) return fft1d(d, src, len, dst, len, len, outer, false, dir, st);
     const bool p2 = is_pow2(len);
-    if (p2 && len <= 4096) {
+    const bool fits31 = (double)len * (double)s < 2147483648.0;   // in-line offsets are 32-bit in the pass kernel
+    if (p2 && len <= 4096 && fits31) {
         int l = ilog2ll(len);
         PassParams p = base_params(d, l);
         p.in = src; p.out = dst; p.nlines = nlines; p.inner = s;
-        p.in_qs = p.out_qs = len * s; p.in_is = p.out_is = 1; p.in_es = p.out_es = s;
+        p.in_qs = p.out_qs = len * s; p.in_is = p.out_is = 1; p.in_es = p.out_es = (int)s;
         p.in_mode = p.out_mode = MODE_COL;
-        if (dir < 0) { p.ld_flags = LD_SWAP; p.st_flags = ST_SWAP | ST_SCALE; p.scale = 1.0 / (double)len; }
+        if (dir < 0) { p.ld_flags = LD_CONJ; p.st_flags = ST_CONJ | ST_SCALE; p.scale = 1.0 / (double)len; }
         return launch_pass(d, l, p, st);
     }
-    if (p2 && len <= (1LL << 24)) {
+    if (p2 && len <= (1LL << 24) && fits31) {
         // strided four-step on blocks of cb adjacent columns; the inter-pass block [len][cb] stays in L2
         const int lg = ilog2ll(len), l1 = (lg + 1) / 2, l2 = lg - l1;
         const long long R1 = 1LL << l1, R2 = 1LL << l2;
@@ -410,19 +470,19 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
                 // pass 1: lines (n2, c): length R1 over n1 (stride R2*s); out block[(k1*R2 + n2)][c]
                 PassParams p = base_params(d, l1);
                 p.in = sp; p.out = scr; p.nlines = R2 * nc; p.inner = nc;
-                p.in_qs = s; p.in_is = 1; p.in_es = R2 * s;
-                p.out_qs = nc; p.out_is = 1; p.out_es = R2 * nc;
+                p.in_qs = s; p.in_is = 1; p.in_es = (int)(R2 * s);
+                p.out_qs = nc; p.out_is = 1; p.out_es = (int)(R2 * nc);
                 p.in_mode = p.out_mode = MODE_COL;
-                if (dir < 0) p.ld_flags = LD_SWAP;
+                if (dir < 0) p.ld_flags = LD_CONJ;
                 p.st_flags = ST_TWIDDLE; p.tw_sel = 1; p.tw_log2m = lg; p.tw_lo = tw.lo; p.tw_hi = tw.hi;
                 GD_TRY(launch_pass(d, l1, p, st));
                 // pass 2: lines (k1, c): length R2 over n2; out row (k1 + R1*k2)
                 PassParams r = base_params(d, l2);
                 r.in = scr; r.out = dp; r.nlines = R1 * nc; r.inner = nc;
-                r.in_qs = R2 * nc; r.in_is = 1; r.in_es = nc;
-                r.out_qs = s; r.out_is = 1; r.out_es = R1 * s;
+                r.in_qs = R2 * nc; r.in_is = 1; r.in_es = (int)nc;
+                r.out_qs = s; r.out_is = 1; r.out_es = (int)(R1 * s);
                 r.in_mode = r.out_mode = MODE_COL;
-                if (dir < 0) { r.st_flags = ST_SWAP | ST_SCALE; r.scale = 1.0 / (double)len; }
+                if (dir < 0) { r.st_flags = ST_CONJ | ST_SCALE; r.scale = 1.0 / (double)len; }
                 GD_TRY(launch_pass(d, l2, r, st));
             }
         return GD_OK;

@@ -62,7 +62,7 @@ struct BluesteinPlan {      // fft/bluestein.go:26-65 cache, plus the cached FFT
     cpx* bhat = nullptr;        // FFT_la(b), la entries
 };
 
-enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OUT, SCR_PWELCH, SCR_AUX, SCR_NSLOTS };
+enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OUT, SCR_PWELCH, SCR_AUX, SCR_CNT, SCR_NSLOTS };
 
 struct Device {
     int dev = -1;
@@ -76,8 +76,14 @@ struct Device {
     std::map<long long, BluesteinPlan> blue;
     void* scratch[SCR_NSLOTS] = {nullptr};
     size_t scratch_bytes[SCR_NSLOTS] = {0};
-    size_t pass_scratch_budget = 48ull << 20;   // inter-pass scratch kept small enough to stay L2-resident
+    size_t pass_scratch_budget = 1ull << 30;    // inter-pass scratch of the two-launch four-step path (chunk of transforms)
     bool wide_tiles = false;             // 512-thread tiles for L >= 1024
+    size_t l2_persist_max = 0;           // cudaDevAttrMaxPersistingL2CacheSize
+    size_t l2_window_max = 0;            // cudaDevAttrMaxAccessPolicyWindowSize
+    bool use_l2_window = true;
+    int fused_delay = 2;                 // phases between P1(g) and P2(g) in the fused schedule
+    bool use_fused = false;              // one persistent kernel for both four-step passes (N = L*L), L2-resident scratch
+    size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     std::recursive_mutex mu;             // every public entry point locks its device
 
     Status init(int device);

@@ -11,6 +11,11 @@
 //                 loops become the pass's address arithmetic);
 //   * Bluestein:  chirp multiply / zero-pad fused into loads, pointwise product and
 //                 post-multiply / truncation fused into stores (fft/bluestein.go:70-93).
+//
+// The lean variant (GENERIC = false) software-pipelines tiles: as soon as the last
+// shared-memory gather of tile t is done, the inputs of tile t+grid are fetched with
+// cp.async (LDGSTS, L2-only) into the now idle exchange buffer, so their latency is
+// hidden behind the last butterfly step, the fused twiddle and the stores of tile t.
 #pragma once
 #include "fft_core.cuh"
 
@@ -21,7 +26,7 @@ enum : int {
     LD_REAL = 1,     // input is float64, imag = 0                     (dsputils.go:25-31 ToComplex)
     LD_PAD = 2,      // elements with local offset >= n_valid_in read as 0 (dsputils.go:49-58 ZeroPad)
     LD_MULAUX = 4,   // multiply by aux_in[local offset]                (bluestein.go:74-76)
-    LD_SWAP = 8,     // swap re/im after the other load ops (inverse transform = swap . forward . swap)
+    LD_CONJ = 8,     // conjugate after the other load ops (inverse = conj . forward . conj)
     LD_REVERSE = 16, // read x[(n_valid_in - n) mod n_valid_in] instead of x[n]  (fft.go:39-43 IFFT index reversal)
 };
 enum : int {
@@ -30,7 +35,7 @@ enum : int {
     ST_SCALE = 4,    // multiply by scale (exact 1/N for power-of-two N; fft.go:47-50)
     ST_DIV = 8,      // divide by div (non power-of-two N keeps the reference's true division)
     ST_TRUNC = 16,   // skip outputs with local offset >= n_valid_out   (bluestein.go:93)
-    ST_SWAP = 32,    // swap re/im before the other store ops
+    ST_CONJ = 32,    // conjugate before the other store ops
 };
 
 struct PassParams {
@@ -38,8 +43,9 @@ struct PassParams {
     void* out;
     long long nlines;          // number of lines in this launch
     long long inner;           // line id = q*inner + i
-    long long in_qs, in_is, in_es;     // element strides: base = q*qs + i*is, element j at + j*es
-    long long out_qs, out_is, out_es;
+    long long in_qs, in_is;    // element strides of the line base: base = q*qs + i*is
+    long long out_qs, out_is;
+    int in_es, out_es;         // element stride inside a line (offsets inside a line fit 31 bits)
     int in_mode, out_mode;     // MODE_ROW: lanes run along the line; MODE_COL: lanes run across adjacent lines
     int ld_flags, st_flags;
     int tw_sel;                // twiddle multiplier: 0 -> i, 1 -> q
@@ -68,6 +74,18 @@ __device__ __forceinline__ cpx tw_lookup(const PassParams& a, unsigned long long
     return cmul(hi, lo);
 }
 
+__device__ __forceinline__ cpx cconj_if(cpx v, unsigned mask) {   // mask = 0 or 0x80000000: one LOP3
+    return make_double2(v.x, __hiloint2double(__double2hiint(v.y) ^ (int)mask, __double2loint(v.y)));
+}
+
+// 16-byte async copy global -> shared, L2-only; bytes = 0 zero-fills the slot
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 // One Stockham step of radix R on the 16 registers of this thread: butterfly q takes
 // x[q + NB*r], its index in the line is j = p + P*q, k = j mod NS.
 template <int L, int R, int NS>
@@ -85,7 +103,9 @@ __device__ __forceinline__ void butterfly_step(cpx (&x)[16], int p, const cpx* _
     }
 }
 
-// scatter the step's outputs into the line's shared-memory region (Stockham auto-sort)
+// scatter the step's outputs into the line's shared-memory region (Stockham auto-sort).
+// pad_idx(base + r*NS) = pad_idx(base) + r*(NS + NS/16) for NS >= 16, and = pad_idx(base) + r
+// for NS == 1 with R == 16: one base index per butterfly, compile-time offsets per output.
 template <int L, int R, int NS>
 __device__ __forceinline__ void scatter_step(const cpx (&x)[16], int p, cpx* __restrict__ sl) {
     constexpr int P = L / 16, NB = 16 / R;
@@ -94,48 +114,95 @@ __device__ __forceinline__ void scatter_step(const cpx (&x)[16], int p, cpx* __r
         int j = p + P * q;
         int k = j & (NS - 1);
         int base = (j - k) * R + k;
+        if constexpr (NS >= 16 || (NS == 1 && R == 16)) {
+            constexpr int RS = NS >= 16 ? NS + (NS >> 4) : 1;
+            cpx* b = sl + pad_idx(base);
 #pragma unroll
-        for (int r = 0; r < R; r++) sl[pad_idx(base + r * NS)] = x[q + NB * r];
+            for (int r = 0; r < R; r++) b[r * RS] = x[q + NB * r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) sl[pad_idx(base + r * NS)] = x[q + NB * r];
+        }
     }
 }
 template <int L>
 __device__ __forceinline__ void gather_step(cpx (&x)[16], int p, const cpx* __restrict__ sl) {
     constexpr int P = L / 16;
+    if constexpr (P >= 16) {
+        const cpx* b = sl + pad_idx(p);
 #pragma unroll
-    for (int i = 0; i < 16; i++) x[i] = sl[pad_idx(p + P * i)];
+        for (int i = 0; i < 16; i++) x[i] = b[i * (P + (P >> 4))];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = sl[pad_idx(p + P * i)];
+    }
+}
+
+// per-tile addressing of one thread
+struct LineRef {
+    long long q, ii;
+    bool valid;
+};
+__device__ __forceinline__ LineRef line_ref(const PassParams& a, long long line) {
+    LineRef r;
+    r.valid = line < a.nlines;
+    r.q = 0; r.ii = 0;
+    if (r.valid) {
+        if (a.inner == 1) r.q = line;
+        else { r.q = line / a.inner; r.ii = line - r.q * a.inner; }
+    }
+    return r;
 }
 
 template <int LOG2L, int T, bool GENERIC>
 __global__ void __launch_bounds__(T * PassShape<LOG2L>::P, (T * PassShape<LOG2L>::P >= 512) ? 1 : 2)
 fft_pass_kernel(const PassParams a) {
     using SH = PassShape<LOG2L>;
-    constexpr int L = SH::L, PPT = SH::PPT, P = SH::P;
+    constexpr int L = SH::L, PPT = SH::PPT, P = SH::P, NT = T * P;
     constexpr int LS = line_stride(L, T);
+    constexpr bool PREFETCH = !GENERIC && LOG2L >= 8;     // T*L == 16*NT and the exchange buffer can hold a tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* sm = reinterpret_cast<cpx*>(smem_raw);
 
     const int tid = threadIdx.x;
     const long long ntiles = (a.nlines + T - 1) / T;
+    const unsigned ld_conj = (a.ld_flags & LD_CONJ) ? 0x80000000u : 0u;
+    // thread -> (line, p) on the load side / store side
+    int ell_in, p_in, ell_out, p_out;
+    if (a.in_mode == MODE_COL) { ell_in = tid % T; p_in = tid / T; } else { p_in = tid % P; ell_in = tid / P; }
+    if (a.out_mode == MODE_COL) { ell_out = tid % T; p_out = tid / T; } else { p_out = tid % P; ell_out = tid / P; }
+    const int in_off0 = p_in * a.in_es, in_step = P * a.in_es;
+    const int out_off0 = p_out * a.out_es, out_step = P * a.out_es;
 
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- thread -> (line, p) for the load side
-        int ell, p;
-        if (a.in_mode == MODE_COL) { ell = tid % T; p = tid / T; } else { p = tid % P; ell = tid / P; }
-        long long line = tile * T + ell;
-        bool valid = line < a.nlines;
-        long long q = 0, ii = 0;
-        if (valid) { q = line / a.inner; ii = line - q * a.inner; }
+    auto prefetch = [&](long long tile) {
+        LineRef lr = line_ref(a, tile * T + ell_in);
+        const cpx* src = reinterpret_cast<const cpx*>(a.in) + lr.q * a.in_qs + lr.ii * a.in_is + in_off0;
+        const int bytes = lr.valid ? 16 : 0;
+        if (!lr.valid) src = reinterpret_cast<const cpx*>(a.in);
+#pragma unroll
+        for (int i = 0; i < 16; i++) cp_async16(sm + i * NT + tid, lr.valid ? src + i * in_step : src, bytes);
+        cp_async_commit();
+    };
 
+    long long tile = blockIdx.x;
+    if constexpr (PREFETCH) { if (tile < ntiles) prefetch(tile); }
+
+    for (; tile < ntiles; tile += gridDim.x) {
         cpx x[16];
         // ---- load
-        {
-            const long long loc0 = ii * a.in_is, base = q * a.in_qs;
+        if constexpr (PREFETCH) {
+            cp_async_wait_all();
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = cconj_if(sm[i * NT + tid], ld_conj);
+        } else {
+            LineRef lr = line_ref(a, tile * T + ell_in);
+            const long long base = lr.q * a.in_qs, loc0 = lr.ii * a.in_is + in_off0;
 #pragma unroll
             for (int i = 0; i < PPT; i++) {
-                long long loc = loc0 + (long long)(p + P * i) * a.in_es;
                 cpx v = make_double2(0.0, 0.0);
                 if constexpr (GENERIC) {
-                    bool ok = valid && !((a.ld_flags & LD_PAD) && loc >= a.n_valid_in);
+                    const long long loc = loc0 + (long long)i * in_step;
+                    bool ok = lr.valid && !((a.ld_flags & LD_PAD) && loc >= a.n_valid_in);
                     if (ok) {
                         long long src = loc;
                         if ((a.ld_flags & LD_REVERSE) && loc != 0) src = a.n_valid_in - loc;
@@ -144,10 +211,9 @@ fft_pass_kernel(const PassParams a) {
                         if (a.ld_flags & LD_MULAUX) v = cmul(v, __ldg(a.aux_in + loc));
                     }
                 } else {
-                    if (valid) v = __ldg(reinterpret_cast<const cpx*>(a.in) + base + loc);
+                    if (lr.valid) v = __ldg(reinterpret_cast<const cpx*>(a.in) + base + loc0 + i * in_step);
                 }
-                if (a.ld_flags & LD_SWAP) v = cswap(v);
-                x[i] = v;
+                x[i] = cconj_if(v, ld_conj);
             }
         }
 
@@ -155,44 +221,33 @@ fft_pass_kernel(const PassParams a) {
         if constexpr (LOG2L <= 4) {
             dft<L, 1>(x);
         } else {
-            cpx* sl = sm + ell * LS;
-            butterfly_step<L, 16, 1>(x, p, a.wl);
-            scatter_step<L, 16, 1>(x, p, sl);
+            cpx* sl = sm + ell_in * LS;
+            butterfly_step<L, 16, 1>(x, p_in, a.wl);
+            if constexpr (PREFETCH) __syncthreads();      // every thread has taken its prefetched inputs
+            scatter_step<L, 16, 1>(x, p_in, sl);
+            __syncthreads();
             if constexpr (SH::NSTEP == 2) {
-                __syncthreads();
-                if (a.out_mode != a.in_mode) {
-                    if (a.out_mode == MODE_COL) { ell = tid % T; p = tid / T; } else { p = tid % P; ell = tid / P; }
-                    sl = sm + ell * LS;
-                }
-                gather_step<L>(x, p, sl);
-                butterfly_step<L, SH::LASTR, 16>(x, p, a.wl);
+                gather_step<L>(x, p_out, sm + ell_out * LS);
             } else {
+                gather_step<L>(x, p_in, sl);
                 __syncthreads();
-                gather_step<L>(x, p, sl);
+                butterfly_step<L, 16, 16>(x, p_in, a.wl);
+                scatter_step<L, 16, 16>(x, p_in, sl);
                 __syncthreads();
-                butterfly_step<L, 16, 16>(x, p, a.wl);
-                scatter_step<L, 16, 16>(x, p, sl);
-                __syncthreads();
-                if (a.out_mode != a.in_mode) {
-                    if (a.out_mode == MODE_COL) { ell = tid % T; p = tid / T; } else { p = tid % P; ell = tid / P; }
-                    sl = sm + ell * LS;
-                }
-                gather_step<L>(x, p, sl);
-                butterfly_step<L, SH::LASTR, 256>(x, p, a.wl);
+                gather_step<L>(x, p_out, sm + ell_out * LS);
             }
-            if (a.out_mode != a.in_mode) {
-                line = tile * T + ell;
-                valid = line < a.nlines;
-                q = 0; ii = 0;
-                if (valid) { q = line / a.inner; ii = line - q * a.inner; }
-            }
+            __syncthreads();                              // exchange buffer is free again
+            if constexpr (PREFETCH) { if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x); }
+            butterfly_step<L, SH::LASTR, (SH::NSTEP == 2 ? 16 : 256)>(x, p_out, a.wl);
         }
+
+        LineRef lo = line_ref(a, tile * T + ell_out);
 
         // ---- fused output twiddle  w_M^(mult * k),  k = p + P*i
         if (a.st_flags & ST_TWIDDLE) {
             unsigned long long mask = (1ULL << a.tw_log2m) - 1ULL;
-            unsigned long long mult = (unsigned long long)(a.tw_sel ? q : ii);
-            cpx t0 = tw_lookup(a, (mult * (unsigned long long)p) & mask);
+            unsigned long long mult = (unsigned long long)(a.tw_sel ? lo.q : lo.ii);
+            cpx t0 = tw_lookup(a, (mult * (unsigned long long)p_out) & mask);
             if constexpr (PPT == 1) {
                 x[0] = cmul(x[0], t0);
             } else {
@@ -219,23 +274,33 @@ fft_pass_kernel(const PassParams a) {
         }
 
         // ---- store
-        if (valid) {
-            const long long loc0 = ii * a.out_is, base = q * a.out_qs;
+        if (lo.valid) {
+            const long long base = lo.q * a.out_qs, loc0 = lo.ii * a.out_is + out_off0;
+            double sx = 1.0, sy = 1.0;
+            if (a.st_flags & ST_SCALE) { sx = a.scale; sy = a.scale; }
+            if (a.st_flags & ST_CONJ) sy = -sy;
+            const bool scaled = a.st_flags & (ST_SCALE | ST_CONJ);
+            cpx* dst = reinterpret_cast<cpx*>(a.out) + base + loc0;
+            if constexpr (GENERIC) {
 #pragma unroll
-            for (int i = 0; i < PPT; i++) {
-                long long loc = loc0 + (long long)(p + P * i) * a.out_es;
-                cpx v = x[i];
-                if (a.st_flags & ST_SWAP) v = cswap(v);
-                if (a.st_flags & ST_SCALE) { v.x *= a.scale; v.y *= a.scale; }
-                if constexpr (GENERIC) {
+                for (int i = 0; i < PPT; i++) {
+                    cpx v = x[i];
+                    if (scaled) { v.x *= sx; v.y *= sy; }
+                    const long long loc = loc0 + (long long)i * out_step;
                     if ((a.st_flags & ST_TRUNC) && loc >= a.n_valid_out) continue;
                     if (a.st_flags & ST_MULAUX) v = cmul(v, __ldg(a.aux_out + loc));
                     if (a.st_flags & ST_DIV) { v.x /= a.div; v.y /= a.div; }
+                    dst[i * out_step] = v;
                 }
-                reinterpret_cast<cpx*>(a.out)[base + loc] = v;
+            } else if (scaled) {                  // uniform branch: no per-element selects
+#pragma unroll
+                for (int i = 0; i < PPT; i++) dst[i * out_step] = make_double2(x[i].x * sx, x[i].y * sy);
+            } else {
+#pragma unroll
+                for (int i = 0; i < PPT; i++) dst[i * out_step] = x[i];
             }
         }
-        if constexpr (LOG2L > 4) __syncthreads();   // shared memory is reused by the next tile
+        if constexpr (LOG2L > 4 && !PREFETCH) __syncthreads();   // shared memory is reused by the next tile
     }
 }
 

@@ -51,7 +51,7 @@ enum gd_status {
 GD_API int gd_init(int ndev);
 GD_API int gd_shutdown(void);
 GD_API const char* gd_last_error(void);
-GD_API int gd_device_count(void);            /* initialised devices */
+GD_API int gd_device_count(void);            /* devices initialised so far */
 GD_API int gd_use_device(int dev);           /* device used by subsequent calls from this thread (default 0) */
 /* Tuning knobs: "pass_scratch_mb" (inter-pass scratch kept L2-resident), "wide_tiles" (0/1). */
 GD_API int gd_set_option(const char* key, int64_t value);

@@ -28,6 +28,10 @@ x = oracle.splitmix_complex(37*1024, 3).reshape(37, 1024); out = np.empty_like(x
 c.check(L.gd_fft_batch_c2c(c.ptr(x), c.ptr(out), 1024, 37, 1)); print("batch 37x1024", rel(out, np.fft.fft(x, axis=1)))
 x = oracle.splitmix_complex(5*(1<<14), 3).reshape(5, 1<<14); out = np.empty_like(x)
 c.check(L.gd_fft_batch_c2c(c.ptr(x), c.ptr(out), 1<<14, 5, 1)); print("batch 5x2^14", rel(out, np.fft.fft(x, axis=1)))
+for (b, lg) in [(7, 16), (3, 18), (5, 20), (70, 16)]:
+    x = oracle.splitmix_complex(b*(1<<lg), 3).reshape(b, 1<<lg); out = np.empty_like(x)
+    c.check(L.gd_fft_batch_c2c(c.ptr(x), c.ptr(out), 1<<lg, b, 1)); e = rel(out, np.fft.fft(x, axis=1))
+    c.check(L.gd_fft_batch_c2c(c.ptr(x), c.ptr(out), 1<<lg, b, -1)); print("batch %dx2^%d" % (b, lg), e, rel(out, np.fft.ifft(x, axis=1)))
 # real
 r = oracle.fill_splitmix(1000, 4); out = np.empty(1000, np.complex128)
 c.check(L.gd_fft_r2c_full(c.ptr(r), c.ptr(out), 1000, 1)); print("fftreal 1000", rel(out, oracle.fft_real(r)))
