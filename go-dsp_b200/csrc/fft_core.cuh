@@ -144,7 +144,7 @@ __host__ __device__ constexpr int line_stride(int L, int T) {
 
 __host__ __device__ constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
 
-// SplitMix64 counter generator (same bits as oracle/godsp_oracle.c gdo_fill_splitmix).
+// SplitMix64 counter generator of the synthetic benchmark inputs.
 __host__ __device__ __forceinline__ double splitmix_unit(uint64_t seed, uint64_t i) {
     uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;

@@ -1,4 +1,6 @@
-"""godsp -- host-side mirror of go-dsp's exported API over the B200 C ABI (see fft.py,
-spectral.py, window.py, dsputils.py). Importing never touches the GPU; every transform
-call does, and fails loudly without one (no CPU fallback)."""
-from . import _capi  # noqa: F401
+"""godsp -- host-side mirror of go-dsp's exported API over the B200 C ABI: packages fft, spectral,
+window and dsputils with the Go names. Importing never touches the GPU; every transform call
+does, and fails loudly without one (there is no CPU fallback)."""
+from . import _capi, _host  # noqa: F401
+from . import dsputils, fft, spectral, window  # noqa: F401
+from ._host import GoPanic  # noqa: F401

@@ -1,0 +1,68 @@
+"""Package fft (fft/fft.go, fft/radix2.go) over the B200 engine. Same names as the Go API."""
+import ctypes as C
+
+import numpy as np
+
+from . import _host
+from .dsputils import Matrix
+
+
+def _c(x):
+    return np.ascontiguousarray(x, dtype=np.complex128)
+
+
+def _run(x, direction, real_in):
+    x = np.ascontiguousarray(x, dtype=np.float64) if real_in else _c(x)
+    if x.ndim != 1:
+        raise ValueError("1-D input expected")
+    out = np.empty(x.shape[0], np.complex128)
+    _host.check(_host.lib().gdh_fft(x.ctypes.data, x.shape[0], out.ctypes.data, direction, int(real_in)))
+    return out
+
+
+def FFT(x): return _run(x, 1, False)            # fft/fft.go:72
+def IFFT(x): return _run(x, -1, False)          # fft/fft.go:35
+def FFTReal(x): return _run(x, 1, True)         # fft/fft.go:25
+def IFFTReal(x): return _run(x, -1, True)       # fft/fft.go:30
+
+
+def Convolve(x, y):                             # fft/fft.go:55
+    x, y = _c(x), _c(y)
+    out = np.empty(max(x.shape[0], 1), np.complex128)
+    _host.check(_host.lib().gdh_convolve(x.ctypes.data, x.shape[0], y.ctypes.data, y.shape[0], out.ctypes.data))
+    return out[: x.shape[0]]
+
+
+def _fft2(x, direction, real_in):
+    """x: a list of rows (like [][]complex128 -- rows may be ragged, which panics as in the reference)."""
+    rows = [np.ascontiguousarray(r, dtype=np.float64 if real_in else np.complex128) for r in x]
+    n = len(rows)
+    outs = [np.empty(len(rows[0]) if n else 0, np.complex128) for _ in rows]
+    VP = C.c_void_p * max(n, 1)
+    I64 = C.c_int64 * max(n, 1)
+    rp, op = VP(*[r.ctypes.data for r in rows]), VP(*[o.ctypes.data for o in outs])
+    ln = I64(*[r.shape[0] for r in rows])
+    _host.check(_host.lib().gdh_fft2(rp, ln, n, op, direction, int(real_in)))
+    return outs
+
+
+def FFT2(x): return _fft2(x, 1, False)          # fft/fft.go:109
+def IFFT2(x): return _fft2(x, -1, False)        # fft/fft.go:119
+def FFT2Real(x): return _fft2(x, 1, True)       # fft/fft.go:104
+def IFFT2Real(x): return _fft2(x, -1, True)     # fft/fft.go:114
+
+
+def _fftn(m, direction):
+    out = np.empty_like(m.list)
+    dims = (C.c_int64 * len(m.dims))(*m.dims)
+    _host.check(_host.lib().gdh_fftn(m.list.ctypes.data, dims, len(m.dims), out.ctypes.data, direction))
+    return Matrix(out, list(m.dims))
+
+
+def FFTN(m): return _fftn(m, 1)                 # fft/fft.go:157
+def IFFTN(m): return _fftn(m, -1)               # fft/fft.go:162
+
+
+def SetWorkerPoolSize(n): _host.lib().gdh_set_worker_pool_size(int(n))          # fft/fft.go:95 (no effect on the GPU)
+def EnsureRadix2Factors(n): _host.check(_host.lib().gdh_ensure_radix2_factors(int(n)))   # fft/radix2.go:35
+def reverseBits(v, s): return int(_host.lib().gdh_reverse_bits(int(v), int(s)))  # fft/radix2.go:184

@@ -1,0 +1,298 @@
+"""GPU parity tests (pytest -m gpu, on the B200 box): the CUDA path, called through the C ABI
+(include/godsp_b200.h) and through the mirror of the Go API, against the CPU oracle on the same
+seeded inputs -- bit-exact for integer results, relative L2 <= 1e-12 for spectra and PSDs
+(BASELINE.json north_star) -- plus the reference's own golden vectors with its own tolerance
+(dsputils.Float64Equal, 1e-8) and size-independent properties at the benchmark sizes."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import cplx, float64_equal, pretty_close, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12                                       # north_star: relative L2 <= 1e-12 (complex128)
+
+
+@pytest.fixture(scope="module")
+def gd():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: these tests must run on the GPU box (there is no CPU fallback)")
+    import godsp
+    from godsp import _capi
+    L = _capi.lib()
+    _capi.check(L.gd_use_device(0))
+    return godsp, _capi, L
+
+
+# ----------------------------------------------------------------- the reference's own test tables
+def test_reference_TestFFT(gd, golden):          # fft/fft_test.go:197-209
+    godsp = gd[0]
+    for c in golden["fft"]["cases"]:
+        x, want = np.array(c["in"], float), cplx(c["out"])
+        assert pretty_close(godsp.fft.FFTReal(x), want), c
+        assert pretty_close(godsp.fft.IFFT(want), x.astype(complex)), c
+
+
+def test_reference_TestFFT2(gd, golden):         # fft/fft_test.go:211-223
+    godsp = gd[0]
+    for c in golden["fft2"]["cases"]:
+        want = cplx(c["out"])
+        v = godsp.fft.FFT2Real(c["in"])
+        assert godsp.dsputils.PrettyClose2(v, list(want))
+        vi = godsp.fft.IFFT2(list(want))
+        assert godsp.dsputils.PrettyClose2(vi, godsp.dsputils.ToComplex2(c["in"]))
+
+
+def test_reference_TestFFTN(gd, golden):         # fft/fft_test.go:225-239
+    godsp = gd[0]
+    for c in golden["fftn"]["cases"]:
+        m = godsp.dsputils.MakeMatrix(godsp.dsputils.ToComplex(c["in"]), c["dim"])
+        o = godsp.dsputils.MakeMatrix(cplx(c["out"]), c["dim"])
+        assert godsp.fft.FFTN(m).PrettyClose(o)
+        assert godsp.fft.IFFTN(o).PrettyClose(m)
+
+
+def test_reference_TestFFTMulti_and_Example(gd, golden):   # fft/fft_test.go:251-259, 283-320
+    godsp = gd[0]
+    n = 256
+    a = (np.arange(n) / n).astype(complex)
+    assert rel_l2(godsp.fft.FFT(a), oracle.fft(a)) <= TOL
+    g = golden["example_fft_real"]
+    x = [math.sin(2 * math.pi * i / 8) + 0.5 * math.sin(2 * math.pi * i / 4 + 3 * math.pi / 4) for i in range(8)]
+    X = godsp.fft.FFTReal(x)
+    for i in range(8):
+        r, th = abs(X[i]), math.degrees(math.atan2(X[i].imag, X[i].real))
+        if float64_equal(r, 0):
+            th = 0.0
+        assert "%.1f" % r == "%.1f" % g["mag"][i] and "%.1f" % th == "%.1f" % g["phase_deg"][i]
+
+
+def test_reference_TestPwelch(gd, golden):       # spectral/pwelch_test.go:48-60
+    godsp = gd[0]
+    for c in golden["pwelch"]["cases"]:
+        p, f = godsp.spectral.Pwelch(np.array(c["x"], float), c["fs"], godsp.spectral.PwelchOptions())
+        assert pretty_close(p, c["p"]) and pretty_close(f, c["freqs"]) and len(p) == len(c["p"])
+
+
+def test_benchmark_input(gd):                    # fft/fft_test.go:262-280 BenchmarkFFT input, N = 2^20
+    godsp = gd[0]
+    n = 1 << 20
+    a = (np.arange(n) / n).astype(complex)
+    godsp.fft.EnsureRadix2Factors(n)
+    assert rel_l2(godsp.fft.FFT(a), oracle.fft(a)) <= TOL
+
+
+# ----------------------------------------------------------------- 1-D transforms vs the oracle
+@pytest.mark.parametrize("lg", list(range(1, 22)))
+def test_pow2_sizes(gd, lg):
+    godsp = gd[0]
+    n = 1 << lg
+    x = oracle.splitmix_complex(n, 1)
+    want = oracle.fft(x)
+    assert rel_l2(godsp.fft.FFT(x), want) <= TOL
+    assert rel_l2(godsp.fft.IFFT(want), x) <= TOL
+    assert rel_l2(godsp.fft.IFFT(x), oracle.ifft(x)) <= TOL
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 6, 7, 9, 12, 100, 255, 1000, 4097, 65537, 100003, 1000003])
+def test_bluestein_sizes(gd, n):                 # config C2 is n = 1,000,003 (la = 2^21)
+    godsp = gd[0]
+    x = oracle.splitmix_complex(n, 2)
+    assert rel_l2(godsp.fft.FFT(x), oracle.fft(x)) <= TOL          # incl. the reference's chirp-phase rounding
+    assert rel_l2(godsp.fft.IFFT(x), oracle.ifft(x)) <= TOL
+    r = oracle.fill_splitmix(n, 4)
+    assert rel_l2(godsp.fft.FFTReal(r), oracle.fft_real(r)) <= TOL
+    assert rel_l2(godsp.fft.IFFTReal(r), oracle.ifft_real(r)) <= TOL
+
+
+def test_real_roundtrips(gd):                    # C2: IFFT(FFTReal(x)) ~ x and FFT(IFFTReal(x)) ~ x
+    godsp = gd[0]
+    for n in (4096, 1000003, 1 << 16):
+        r = oracle.fill_splitmix(n, 7)
+        assert rel_l2(godsp.fft.IFFT(godsp.fft.FFTReal(r)), r.astype(complex)) <= 1e-9 if n == 1000003 else TOL * 10
+        assert rel_l2(godsp.fft.FFT(godsp.fft.IFFTReal(r)), r.astype(complex)) <= 1e-9 if n == 1000003 else TOL * 10
+
+
+def test_bluestein_padding_lengths(gd):
+    L = gd[2]
+    for n in (3, 5, 1000, 65537, 1000003):
+        assert L.gd_bluestein_padded_len(n) == oracle.bluestein_padded_len(n)
+
+
+@pytest.mark.parametrize("n", [8, 48, 1000, 4096, 1 << 15])
+def test_convolve(gd, n):
+    godsp = gd[0]
+    x, y = oracle.splitmix_complex(n, 1), oracle.splitmix_complex(n, 2)
+    assert rel_l2(godsp.fft.Convolve(x, y), oracle.convolve(x, y)) <= TOL
+
+
+@pytest.mark.parametrize("b,lg", [(37, 10), (5, 14), (7, 16), (3, 18), (5, 20), (300, 5), (1000, 1), (70, 16)])
+def test_batched(gd, b, lg):
+    _, capi, L = gd
+    n = 1 << lg
+    x = oracle.splitmix_complex(b * n, 3).reshape(b, n)
+    want = oracle.fft_batch(x, threads=8)
+    out = np.empty_like(x)
+    capi.check(L.gd_fft_batch_c2c(x.ctypes.data, out.ctypes.data, n, b, 1))
+    assert rel_l2(out, want) <= TOL
+    capi.check(L.gd_fft_batch_c2c(want.ctypes.data, out.ctypes.data, n, b, -1))
+    assert rel_l2(out, x) <= TOL
+
+
+@pytest.mark.parametrize("opt", [("fused", 1), ("wide_tiles", 1), ("pass_scratch_mb", 16)])
+def test_alternative_schedules_agree(gd, opt):   # every planner variant must give the same transform
+    _, capi, L = gd
+    x = oracle.splitmix_complex(6 << 20, 3).reshape(6, 1 << 20)
+    want = oracle.fft_batch(x, threads=8)
+    out = np.empty_like(x)
+    capi.check(L.gd_set_option(opt[0].encode(), opt[1]))
+    try:
+        capi.check(L.gd_fft_batch_c2c(x.ctypes.data, out.ctypes.data, 1 << 20, 6, 1))
+    finally:
+        capi.check(L.gd_set_option(opt[0].encode(), {"fused": 0, "wide_tiles": 0, "pass_scratch_mb": 1024}[opt[0]]))
+    assert rel_l2(out, want) <= TOL
+
+
+# ----------------------------------------------------------------- FFT2 / FFTN
+@pytest.mark.parametrize("shape", [(2, 3), (3, 5), (64, 32), (300, 7), (8192, 16), (16, 8192), (512, 512),
+                                   (2, 2, 3), (4, 6, 8, 5), (16, 16, 16), (3, 1, 4)])
+def test_fftn_shapes(gd, shape):
+    godsp = gd[0]
+    x = oracle.splitmix_complex(int(np.prod(shape)), 4).reshape(shape)
+    m = godsp.dsputils.MakeMatrix(x.ravel(), list(shape))
+    assert rel_l2(godsp.fft.FFTN(m).list, oracle.fftn(x).ravel()) <= TOL
+    assert rel_l2(godsp.fft.IFFTN(m).list, oracle.fftn(x, inverse=True).ravel()) <= TOL
+    if len(shape) == 2:
+        got = np.stack(godsp.fft.FFT2(list(x)))
+        assert rel_l2(got, oracle.fft2(x)) <= TOL
+
+
+def test_fft2_large_rows_cols(gd):               # 2^14-long lines in both axes (the C3 matrix is 16384^2)
+    _, capi, L = gd
+    for rows, cols in ((16384, 32), (32, 16384)):
+        x = oracle.splitmix_complex(rows * cols, 4).reshape(rows, cols)
+        out = np.empty_like(x)
+        capi.check(L.gd_fft2_c2c(x.ctypes.data, out.ctypes.data, rows, cols, 1))
+        assert rel_l2(out, oracle.fft2(x)) <= TOL
+
+
+# ----------------------------------------------------------------- Pwelch
+PW_CASES = [  # (nx, NFFT, Noverlap, Pad, window, scale_off)
+    (100, 0, 0, 0, None, False), (5000, 256, 128, 0, None, False), (100000, 4096, 2048, 0, "Hann", False),
+    (50000, 1024, 512, 2048, "Hamming", False), (5000, 100, 30, 0, "Blackman", True), (5000, 256, 0, 128, "FlatTop", False),
+    (9000, 4096, 2048, 0, "Bartlett", False), (70000, 64, 63, 0, "Rectangular", False), (33000, 2048, 1024, 0, None, True),
+    (40000, 512, 100, 0, None, False), (4096, 4096, 0, 0, None, False), (20000, 32, 16, 0, None, False),
+    (20000, 6000, 3000, 0, None, False), (3000, 300, 0, 1000, None, False),
+]
+
+
+@pytest.mark.parametrize("case", PW_CASES)
+def test_pwelch_options(gd, case):
+    godsp = gd[0]
+    nx, nfft, nov, pad, wname, soff = case
+    x = oracle.fill_splitmix(nx, 5)
+    w = getattr(godsp.window, wname) if wname else None
+    p, f = godsp.spectral.Pwelch(x, 2.0, godsp.spectral.PwelchOptions(NFFT=nfft, Window=w, Pad=pad, Noverlap=nov, Scale_off=soff))
+    pw, fw = oracle.pwelch(x, 2.0, nfft=nfft, pad=pad, noverlap=nov, window_fn=(wname or "hann").lower(), scale_off=soff)
+    assert len(p) == len(pw)                                    # bin count, bit-exact
+    assert np.array_equal(f.view(np.uint64), fw.view(np.uint64))   # frequency vector, bit-exact
+    assert rel_l2(p, pw) <= TOL
+
+
+def test_pwelch_custom_window_closure(gd):       # PwelchOptions.Window is an arbitrary function (pwelch.go:41)
+    godsp = gd[0]
+    wf = lambda n: np.cos(np.arange(n) / max(n, 1)) ** 2 + 0.1
+    x = oracle.fill_splitmix(30000, 5)
+    p, f = godsp.spectral.Pwelch(x, 3.0, godsp.spectral.PwelchOptions(NFFT=1024, Window=wf, Noverlap=256))
+    pw, fw = oracle.pwelch(x, 3.0, nfft=1024, noverlap=256, window_fn=wf)
+    assert rel_l2(p, pw) <= TOL and np.array_equal(f, fw)
+
+
+def test_pwelch_config4_sample(gd):              # C4 shape (NFFT 4096, 50% overlap, Hann) on 2^24 samples vs the oracle
+    godsp = gd[0]
+    x = oracle.fill_splitmix(1 << 24, 5)
+    p, f = godsp.spectral.Pwelch(x, 1.0, godsp.spectral.PwelchOptions(NFFT=4096, Noverlap=2048, Window=godsp.window.Hann))
+    pw, fw = oracle.pwelch(x, 1.0, nfft=4096, noverlap=2048, threads=8)
+    assert len(p) == 2049 and np.array_equal(f, fw) and rel_l2(p, pw) <= TOL
+
+
+# ----------------------------------------------------------------- properties at benchmark sizes (device-resident)
+def test_full_size_properties(gd):
+    """2^20-point batch of 256 on the device: impulse known answers, linearity, Parseval, and
+    rows checked against the oracle; Pwelch on 2^28 samples: segment count, Parseval-type checksum."""
+    import torch
+    _, capi, L = gd
+    n, b = 1 << 20, 256
+    x = torch.empty(b * n * 2, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    st = C.c_void_p(0)
+    capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), b * n * 2, 3, 0, st))
+    capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, b, 1, st))
+    capi.check(L.gd_stream_sync(st))
+    xc, yc = torch.view_as_complex(x.view(-1, 2)).view(b, n), torch.view_as_complex(y.view(-1, 2)).view(b, n)
+    # Parseval per row: sum|X|^2 = N sum|x|^2
+    ex, ey = (xc.abs() ** 2).sum(1), (yc.abs() ** 2).sum(1)
+    assert float(((ey / n - ex).abs() / ex).max()) < 1e-13
+    # sampled rows against the oracle (row r uses counters from 2*r*n)
+    for r in (0, 100, 255):
+        want = oracle.fft(oracle.splitmix_complex(n, 3, r * n))
+        assert rel_l2(yc[r].cpu().numpy(), want) <= TOL
+    # inverse round trip on the device
+    z = torch.empty_like(x)
+    capi.check(L.gd_fft_batch_c2c_dev(y.data_ptr(), z.data_ptr(), n, b, -1, st))
+    capi.check(L.gd_stream_sync(st))
+    assert float((z - x).norm() / x.norm()) < 1e-14
+    # impulse at p -> exp(-2 pi i p k / N)
+    x.zero_()
+    xv = x.view(b, n, 2)
+    ps = [0, 1, 12345, n - 1]
+    for i, p in enumerate(ps):
+        xv[i, p, 0] = 1.0
+    capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, b, 1, st))
+    capi.check(L.gd_stream_sync(st))
+    k = torch.arange(n, device="cuda", dtype=torch.float64)
+    for i, p in enumerate(ps):
+        ang = -2 * math.pi * ((k * p) % n) / n
+        want = torch.complex(torch.cos(ang), torch.sin(ang))
+        assert float((yc[i] - want).abs().max()) < 1e-12
+    assert float(yc[len(ps):].abs().max()) == 0.0
+    del x, y, z
+    # Pwelch, 2^28 samples resident: total power check  sum(Pxx)*Fs/NFFT ~ var(x) and sharded == unsharded
+    ns, nfft, nov = 1 << 28, 4096, 2048
+    s = torch.empty(ns, dtype=torch.float64, device="cuda")
+    capi.check(L.gd_fill_splitmix_dev(s.data_ptr(), ns, 5, 0, st))
+    win = oracle.window("hann", nfft)
+    norm = float(np.sum(win ** 2))
+    dwin = torch.from_numpy(win).cuda()
+    lp, nsegs = nfft // 2 + 1, oracle.segment_count(ns, nfft, nov)
+    assert nsegs == 131071
+    raw, raw2, pxx = (torch.empty(lp, dtype=torch.float64, device="cuda") for _ in range(3))
+    capi.check(L.gd_pwelch_partial_dev(s.data_ptr(), nfft, nov, nfft, lp, 0, nsegs, dwin.data_ptr(), raw.data_ptr(), st))
+    capi.check(L.gd_pwelch_finalize_dev(raw.data_ptr(), lp, nsegs, norm, pxx.data_ptr(), st))
+    capi.check(L.gd_stream_sync(st))
+    total_power = float(pxx.sum()) / nfft
+    assert abs(total_power - 1.0 / 3.0) < 2e-4                   # uniform [-1,1): variance 1/3
+    # two "ranks": segment ranges [0, h) and [h, nsegs) summed in order equal the single range
+    h = nsegs // 2
+    capi.check(L.gd_pwelch_partial_dev(s.data_ptr(), nfft, nov, nfft, lp, 0, h, dwin.data_ptr(), raw2.data_ptr(), st))
+    capi.check(L.gd_pwelch_partial_dev(s.data_ptr(), nfft, nov, nfft, lp, h, nsegs - h, dwin.data_ptr(), pxx.data_ptr(), st))
+    capi.check(L.gd_stream_sync(st))
+    assert float(((raw2 + pxx) - raw).norm() / raw.norm()) < 1e-13
+
+
+def test_edge_cases(gd):
+    godsp = gd[0]
+    assert len(godsp.fft.FFT(np.zeros(0))) == 0                   # fft/fft.go:76-80
+    assert godsp.fft.FFT(np.array([3 + 4j]))[0] == 3 + 4j
+    assert godsp.fft.IFFT(np.array([3 + 4j]))[0] == 3 + 4j
+    with pytest.raises(godsp.GoPanic):
+        godsp.fft.IFFT(np.zeros(0))                               # index out of range in the reference (fft.go:40)
+    x = oracle.splitmix_complex(64, 9)
+    keep = x.copy()
+    godsp.fft.FFT(x)
+    assert np.array_equal(x, keep)                                # inputs are never modified
+    assert gd[2].gd_kernel_launches() > 0
