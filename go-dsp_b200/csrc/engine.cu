@@ -11,8 +11,8 @@
 
 namespace gd {
 
-cudaError_t launch_fused(int log2l, const FusedParams& a, long long total_items, int num_sms, cudaStream_t st);
-int fused_tile_lines(int log2l);
+cudaError_t launch_fused(int log2l, bool wide, const FusedParams& a, long long total_items, int num_sms, cudaStream_t st);
+int fused_tile_lines(int log2l, bool wide);
 
 // ------------------------------------------------------------------ errors
 std::atomic<long long> g_launches{0};
@@ -68,7 +68,6 @@ Status Device::init(int device) {
     num_sms = prop.multiProcessorCount;
     l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-    if (l2_persist_max) GD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max));
     GD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     GD_CUDA(cudaStreamCreateWithFlags(&stream_in, cudaStreamNonBlocking));
     GD_CUDA(cudaStreamCreateWithFlags(&stream_out, cudaStreamNonBlocking));
@@ -184,7 +183,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
     const bool lean = !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
     if (d.use_fused && lean && (log2n % 2) == 0 && log2n >= 16 && batch * (2LL << (log2n / 2)) < (1LL << 30)) {
         // both passes in one persistent kernel, intermediate resident in L2 (fft_fused.cuh)
-        const int l = log2n / 2, T = fused_tile_lines(l), tpt = (1 << l) / T;
+        const int l = log2n / 2, T = fused_tile_lines(l, d.wide_tiles), tpt = (1 << l) / T;
         TwiddleTable tw;
         GD_TRY(d.twiddles(log2n, &tw));
         long long J = (2LL * d.num_sms * 2 + tpt - 1) / tpt;               // ~2 rounds of resident CTAs per phase
@@ -209,18 +208,26 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         // keep the scratch slots resident in L2: persisting access-policy window for this launch
         const size_t scr_bytes = (size_t)(d.fused_delay + 2) * J * N * sizeof(cpx);
         const bool window = d.use_l2_window && d.l2_persist_max > 0 && d.l2_window_max > 0;
+        if (window) {      // carve a persisting set-aside just large enough for the scratch slots (the rest of L2
+                           // keeps merging the partial-line stores of the streaming side)
+            size_t want = scr_bytes < d.l2_persist_max ? scr_bytes : d.l2_persist_max;
+            if (d.l2_carved != want) {
+                GD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+                d.l2_carved = want;
+            }
+        }
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
         if (window) {
             attr.accessPolicyWindow.base_ptr = f.scratch;
             attr.accessPolicyWindow.num_bytes = scr_bytes < d.l2_window_max ? scr_bytes : d.l2_window_max;
-            double ratio = (double)d.l2_persist_max / (double)attr.accessPolicyWindow.num_bytes;
+            double ratio = (double)d.l2_carved / (double)attr.accessPolicyWindow.num_bytes;
             attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             GD_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
         }
-        cudaError_t e = launch_fused(l, f, total_items, d.num_sms, st);
+        cudaError_t e = launch_fused(l, d.wide_tiles, f, total_items, d.num_sms, st);
         if (window) {
             attr.accessPolicyWindow.num_bytes = 0;
             cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);

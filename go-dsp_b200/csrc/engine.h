@@ -81,6 +81,7 @@ struct Device {
     size_t l2_persist_max = 0;           // cudaDevAttrMaxPersistingL2CacheSize
     size_t l2_window_max = 0;            // cudaDevAttrMaxAccessPolicyWindowSize
     bool use_l2_window = true;
+    size_t l2_carved = 0;                // current cudaLimitPersistingL2CacheSize on this device
     int fused_delay = 2;                 // phases between P1(g) and P2(g) in the fused schedule
     bool use_fused = false;              // one persistent kernel for both four-step passes (N = L*L), L2-resident scratch
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)

@@ -13,6 +13,7 @@
 // The scratch slots are covered by a persisting L2 access-policy window (set by the host) and the
 // output stores are streaming (st.global.cs), so HBM sees ~32 B/point (the algorithmic minimum), not 64.
 #pragma once
+#include <stdio.h>
 #include "fft_pass.cuh"
 
 namespace gd {
@@ -168,9 +169,13 @@ fft_fused_kernel(const FusedParams a) {
         // instead of holding every phase back); the atomic's round trip overlaps the first butterfly step
         int claimed = 0;
         if (tid == 0) claimed = (int)gridDim.x + atomicAdd(a.next_item, 1);
+        long long ck[8];
+        const bool tr = (a.debug & 16) && tid == 64 && (blockIdx.x == 0 || blockIdx.x == 200);
+        if (tr) ck[0] = clock64();
 
         cpx x[16];
         cp_async_wait_all();
+        if (tr) ck[1] = clock64();
 #pragma unroll
         for (int i = 0; i < 16; i++) x[i] = sm[i * NT + tid];
         if (cur.type == 0) {
@@ -188,13 +193,17 @@ fft_fused_kernel(const FusedParams a) {
                 if (c) probe = ld_relaxed(c);
             }
         }
+        if (tr) ck[2] = clock64();
         __syncthreads();                          // every thread has taken its prefetched inputs; s_next visible
+        if (tr) ck[3] = clock64();
         const int gn = s_next;
         const bool have_next = gn < total;
         const FusedItem nxt = decode(gn);
-        if (pend_valid && tid == 0) publish(pend);   // previous tile: its stores precede the barrier above
         scatter_step<L, 16, 1>(x, p, sl);
         __syncthreads();
+        // publish the previous tile from the LAST warp (the first one carries the queue / probe duties), here
+        // where a long compute section follows: the release fence's round trip hides behind step 2
+        if (pend_valid && tid == NT - 32) publish(pend);
         gather_step<L>(x, p, sl);
         if constexpr (SH::NSTEP == 3) {
             __syncthreads();
@@ -210,7 +219,9 @@ fft_fused_kernel(const FusedParams a) {
             }
             s_ready = (have_next && probe >= need && !(a.debug & 1)) ? 1 : 0;
         }
+        if (tr) ck[4] = clock64();
         __syncthreads();                          // exchange buffer is free again; s_ready visible
+        if (tr) ck[5] = clock64();
         const bool early = s_ready != 0;
         if (early) prefetch(nxt);
         butterfly_step<L, SH::LASTR, (SH::NSTEP == 2 ? 16 : 256)>(x, p, a.wl);
@@ -253,13 +264,18 @@ fft_fused_kernel(const FusedParams a) {
                 for (int i = 0; i < 16; i++) __stcs(dst + (long long)i * (P * L), x[i]);
             }
         }
+        if (tr) {
+            ck[6] = clock64();
+            printf("cta %d type %d grp %d tile %d early %d | wait %lld ld+bf1 %lld bar1 %lld mid %lld bar5 %lld tail %lld total %lld\n", blockIdx.x, cur.type,
+                   cur.group, cur.tile, (int)early, ck[1] - ck[0], ck[2] - ck[1], ck[3] - ck[2], ck[4] - ck[3], ck[5] - ck[4], ck[6] - ck[5], ck[6] - ck[0]);
+        }
         pend = cur;
         pend_valid = true;
         if (!have_next) break;
         if (!early) {
             // never block while holding an unpublished tile
             __syncthreads();
-            if (tid == 0) publish(pend);
+            if (tid == NT - 32) publish(pend);
             pend_valid = false;
             wait_dep(nxt);
             prefetch(nxt);
@@ -267,7 +283,7 @@ fft_fused_kernel(const FusedParams a) {
         cur = nxt;
     }
     __syncthreads();
-    if (tid == 0) publish(pend);
+    if (tid == NT - 32) publish(pend);
 }
 
 }  // namespace gd

@@ -24,7 +24,8 @@ static cudaError_t launch_fused_impl(const FusedParams& a, long long total_items
     return cudaGetLastError();
 }
 
-cudaError_t launch_fused(int log2l, const FusedParams& a, long long total_items, int num_sms, cudaStream_t st) {
+cudaError_t launch_fused(int log2l, bool wide, const FusedParams& a, long long total_items, int num_sms, cudaStream_t st) {
+    if (wide && log2l == 10) return launch_fused_impl<10, 8>(a, total_items, num_sms, st);
     switch (log2l) {
         case 8: return launch_fused_impl<8, 16>(a, total_items, num_sms, st);
         case 9: return launch_fused_impl<9, 8>(a, total_items, num_sms, st);
@@ -34,5 +35,5 @@ cudaError_t launch_fused(int log2l, const FusedParams& a, long long total_items,
     }
     return cudaErrorInvalidValue;
 }
-int fused_tile_lines(int log2l) { return pass_tile_lines(log2l, false); }
+int fused_tile_lines(int log2l, bool wide) { return pass_tile_lines(log2l, wide && log2l == 10); }
 }  // namespace gd

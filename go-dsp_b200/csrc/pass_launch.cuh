@@ -2,6 +2,7 @@
 #pragma once
 #include "fft_pass.cuh"
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 namespace gd {
 
@@ -23,6 +24,7 @@ cudaError_t launch_pass_impl(const PassParams& a, int num_sms, cudaStream_t st) 
     if (!info.ready) {
         info.threads = T * SH::P;
         info.smem = LOG2L > 4 ? T * line_stride(SH::L, T) * (int)sizeof(cpx) : 0;
+        if (const char* ex = getenv("GD_EXTRA_SMEM_KB")) info.smem += atoi(ex) * 1024;   // occupancy experiments
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, info.smem);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&info.blocks_per_sm, kern, info.threads, info.smem);
