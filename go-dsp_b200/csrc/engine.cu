@@ -82,6 +82,7 @@ Status Device::init(int device) {
     }
     if (const char* s = getenv("GD_WIDE_TILES")) wide_tiles = atoi(s) != 0;
     if (const char* s = getenv("GD_FUSED")) use_fused = atoi(s) != 0;
+    if (const char* s = getenv("GD_TILED")) tiled_scratch = atoi(s) != 0;
     if (const char* s = getenv("GD_L2_WINDOW")) use_l2_window = atoi(s) != 0;
     if (const char* s = getenv("GD_FUSED_DELAY")) { int v = atoi(s); if (v >= 1 && v <= 6) fused_delay = v; }
     if (getenv("GD_VERBOSE")) fprintf(stderr, "[godsp] dev %d: %d SMs, L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", dev, num_sms, prop.l2CacheSize >> 20, l2_persist_max >> 20, l2_window_max >> 20);
@@ -249,7 +250,10 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
     const bool real_in = ops.ld_flags & LD_REAL;
     for (long long b0 = 0; b0 < batch; b0 += chunk) {
         long long nb = batch - b0 < chunk ? batch - b0 : chunk;
-        // pass 1: columns n2 of every transform, length N1, twiddle w_N^(n2*k1) on store
+        // pass 1: columns n2 of every transform, length N1, twiddle w_N^(n2*k1) on store; the intermediate
+        // is tile-major (T adjacent columns = one contiguous block) so these stores are fully coalesced
+        const int T1 = pass_tile_lines(l1, d.wide_tiles), T2 = pass_tile_lines(l2, d.wide_tiles);
+        const bool tiled = d.tiled_scratch && T1 == T2 && ((N2 / 16) % T1) == 0 && !(ops.st_flags & ~(ST_CONJ | ST_SCALE)) ;
         PassParams p = base_params(d, l1);
         p.in = real_in ? (const void*)((const double*)in + b0 * in_dist) : (const void*)((const cpx*)in + b0 * in_dist);
         p.out = scr;
@@ -259,6 +263,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         p.in_mode = p.out_mode = MODE_COL;
         p.ld_flags = ops.ld_flags; p.aux_in = ops.aux_in; p.n_valid_in = ops.n_valid_in;
         p.st_flags = ST_TWIDDLE; p.tw_sel = 0; p.tw_log2m = log2n; p.tw_lo = tw.lo; p.tw_hi = tw.hi;
+        if (tiled) { p.out_tiled = 1; p.tiled_len = (int)N1; }
         GD_TRY(launch_pass(d, l1, p, st));
         // pass 2: rows k1, length N2, transposed store X[k1 + N1*k2]
         PassParams r = base_params(d, l2);
@@ -267,6 +272,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         r.in_qs = N; r.in_is = N2; r.in_es = 1;
         r.out_qs = out_dist; r.out_is = 1; r.out_es = (int)N1;
         r.in_mode = MODE_ROW; r.out_mode = MODE_COL;
+        if (tiled) { r.in_tiled = 1; r.tiled_len = (int)N1; r.in_mode = MODE_COL; }
         r.st_flags = ops.st_flags; r.aux_out = ops.aux_out; r.n_valid_out = ops.n_valid_out;
         r.scale = ops.scale; r.div = ops.div;
         GD_TRY(launch_pass(d, l2, r, st));

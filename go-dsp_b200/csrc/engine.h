@@ -78,6 +78,7 @@ struct Device {
     size_t scratch_bytes[SCR_NSLOTS] = {0};
     size_t pass_scratch_budget = 1ull << 30;    // inter-pass scratch of the two-launch four-step path (chunk of transforms)
     bool wide_tiles = false;             // 512-thread tiles for L >= 1024
+    bool tiled_scratch = false;          // tile-major four-step intermediate (measured slower: pass 2 loses its contiguous row reads)
     size_t l2_persist_max = 0;           // cudaDevAttrMaxPersistingL2CacheSize
     size_t l2_window_max = 0;            // cudaDevAttrMaxAccessPolicyWindowSize
     bool use_l2_window = true;

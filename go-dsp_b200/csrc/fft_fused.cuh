@@ -169,13 +169,18 @@ fft_fused_kernel(const FusedParams a) {
         // instead of holding every phase back); the atomic's round trip overlaps the first butterfly step
         int claimed = 0;
         if (tid == 0) claimed = (int)gridDim.x + atomicAdd(a.next_item, 1);
+#ifdef GD_FUSED_TRACE
         long long ck[8];
         const bool tr = (a.debug & 16) && tid == 64 && (blockIdx.x == 0 || blockIdx.x == 200);
         if (tr) ck[0] = clock64();
+#define GD_CK(i) if (tr) ck[i] = clock64()
+#else
+#define GD_CK(i)
+#endif
 
         cpx x[16];
         cp_async_wait_all();
-        if (tr) ck[1] = clock64();
+        GD_CK(1);
 #pragma unroll
         for (int i = 0; i < 16; i++) x[i] = sm[i * NT + tid];
         if (cur.type == 0) {
@@ -193,9 +198,9 @@ fft_fused_kernel(const FusedParams a) {
                 if (c) probe = ld_relaxed(c);
             }
         }
-        if (tr) ck[2] = clock64();
+        GD_CK(2);
         __syncthreads();                          // every thread has taken its prefetched inputs; s_next visible
-        if (tr) ck[3] = clock64();
+        GD_CK(3);
         const int gn = s_next;
         const bool have_next = gn < total;
         const FusedItem nxt = decode(gn);
@@ -219,23 +224,32 @@ fft_fused_kernel(const FusedParams a) {
             }
             s_ready = (have_next && probe >= need && !(a.debug & 1)) ? 1 : 0;
         }
-        if (tr) ck[4] = clock64();
+        GD_CK(4);
         __syncthreads();                          // exchange buffer is free again; s_ready visible
-        if (tr) ck[5] = clock64();
+        GD_CK(5);
         const bool early = s_ready != 0;
-        if (early) prefetch(nxt);
-        butterfly_step<L, SH::LASTR, (SH::NSTEP == 2 ? 16 : 256)>(x, p, a.wl);
-
-        const int j = cur.tf - cur.group * a.group_tf;
+        // twiddle loads of the tail go out BEFORE the prefetch burst (they would queue behind it otherwise)
+        constexpr int LNS = SH::NSTEP == 2 ? 16 : 256;
+        cpx wlast[16 / SH::LASTR];
+        load_step_twiddles<L, SH::LASTR, LNS>(wlast, p, a.wl);
+        cpx tw0 = make_double2(1.0, 0.0), tws = make_double2(1.0, 0.0);
         if (cur.type == 0) {
-            // fused twiddle w_N^(n2*k1), k1 = p + P*i
             const unsigned long long mask = (1ULL << a.log2n) - 1ULL;
             const unsigned long long n2 = (unsigned long long)(cur.tile * T + ell);
             PassParams tp;                         // only the twiddle fields are used by tw_lookup
             tp.tw_log2m = a.log2n; tp.tw_lo = a.tw_lo; tp.tw_hi = a.tw_hi;
+            tw0 = tw_lookup(tp, (n2 * (unsigned long long)p) & mask);
+            tws = tw_lookup(tp, (n2 * (unsigned long long)P) & mask);
+        }
+        if (early) prefetch(nxt);
+        butterfly_step_w<L, SH::LASTR, LNS>(x, wlast);
+
+        const int j = cur.tf - cur.group * a.group_tf;
+        if (cur.type == 0) {
+            // fused twiddle w_N^(n2*k1), k1 = p + P*i  (base tw0 and step tws were looked up above)
             cpx t[16];
-            t[0] = tw_lookup(tp, (n2 * (unsigned long long)p) & mask);
-            cpx s1 = tw_lookup(tp, (n2 * (unsigned long long)P) & mask);
+            t[0] = tw0;
+            const cpx s1 = tws;
             t[1] = cmul(t[0], s1);
             cpx s2 = csqr(s1);
             t[2] = cmul(t[0], s2); t[3] = cmul(t[1], s2);
@@ -264,11 +278,13 @@ fft_fused_kernel(const FusedParams a) {
                 for (int i = 0; i < 16; i++) __stcs(dst + (long long)i * (P * L), x[i]);
             }
         }
+#ifdef GD_FUSED_TRACE
         if (tr) {
             ck[6] = clock64();
             printf("cta %d type %d grp %d tile %d early %d | wait %lld ld+bf1 %lld bar1 %lld mid %lld bar5 %lld tail %lld total %lld\n", blockIdx.x, cur.type,
                    cur.group, cur.tile, (int)early, ck[1] - ck[0], ck[2] - ck[1], ck[3] - ck[2], ck[4] - ck[3], ck[5] - ck[4], ck[6] - ck[5], ck[6] - ck[0]);
         }
+#endif
         pend = cur;
         pend_valid = true;
         if (!have_next) break;

@@ -47,6 +47,11 @@ struct PassParams {
     long long out_qs, out_is;
     int in_es, out_es;         // element stride inside a line (offsets inside a line fit 31 bits)
     int in_mode, out_mode;     // MODE_ROW: lanes run along the line; MODE_COL: lanes run across adjacent lines
+    // Tile-major four-step intermediate: element (k, line i) of a transform lives at
+    // (i/T)*T*tiled_len + k*T + i%T, so a pass-1 tile (T adjacent columns) is one contiguous block.
+    // out_tiled: this pass writes it (lines = columns i, element k).  in_tiled: this pass reads it
+    // (lines = rows k, element i); both need MODE_COL. tiled_len = number of rows (N1).
+    int out_tiled, in_tiled, tiled_len;
     int ld_flags, st_flags;
     int tw_sel;                // twiddle multiplier: 0 -> i, 1 -> q
     int tw_log2m;              // M = 2^tw_log2m
@@ -99,6 +104,27 @@ __device__ __forceinline__ void butterfly_step(cpx (&x)[16], int p, const cpx* _
             cpx w = __ldg(wl + k * (L / (NS * R)));
             twiddle_powers<R, NB>(&x[q], w);
         }
+        dft<R, NB>(&x[q]);
+    }
+}
+
+// The same step with its twiddle bases loaded separately (so the loads can be issued ahead of a
+// burst of prefetch copies instead of queueing behind them in the load/store unit).
+template <int L, int R, int NS>
+__device__ __forceinline__ void load_step_twiddles(cpx (&w)[16 / R], int p, const cpx* __restrict__ wl) {
+    constexpr int P = L / 16, NB = 16 / R;
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+        int k = (p + P * q) & (NS - 1);
+        w[q] = __ldg(wl + k * (L / (NS * R)));
+    }
+}
+template <int L, int R, int NS>
+__device__ __forceinline__ void butterfly_step_w(cpx (&x)[16], const cpx (&w)[16 / R]) {
+    constexpr int NB = 16 / R;
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+        twiddle_powers<R, NB>(&x[q], w[q]);
         dft<R, NB>(&x[q]);
     }
 }
@@ -171,12 +197,19 @@ fft_pass_kernel(const PassParams a) {
     int ell_in, p_in, ell_out, p_out;
     if (a.in_mode == MODE_COL) { ell_in = tid % T; p_in = tid / T; } else { p_in = tid % P; ell_in = tid / P; }
     if (a.out_mode == MODE_COL) { ell_out = tid % T; p_out = tid / T; } else { p_out = tid % P; ell_out = tid / P; }
-    const int in_off0 = p_in * a.in_es, in_step = P * a.in_es;
-    const int out_off0 = p_out * a.out_es, out_step = P * a.out_es;
+    int in_off0 = p_in * a.in_es, in_step = P * a.in_es;
+    int out_off0 = p_out * a.out_es, out_step = P * a.out_es;
+    if (a.in_tiled) { in_off0 = (p_in / T) * (T * a.tiled_len) + (p_in % T); in_step = P * a.tiled_len; }
+    if (a.out_tiled) { out_off0 = p_out * T; out_step = P * T; }
+    // line-base offset inside a transform: plain i*is, or the tile-major forms
+    auto in_line = [&](long long ii) -> long long { return a.in_tiled ? ii * T : ii * a.in_is; };
+    auto out_line = [&](long long ii) -> long long {
+        return a.out_tiled ? (ii / T) * ((long long)T * a.tiled_len) + (ii % T) : ii * a.out_is;
+    };
 
     auto prefetch = [&](long long tile) {
         LineRef lr = line_ref(a, tile * T + ell_in);
-        const cpx* src = reinterpret_cast<const cpx*>(a.in) + lr.q * a.in_qs + lr.ii * a.in_is + in_off0;
+        const cpx* src = reinterpret_cast<const cpx*>(a.in) + lr.q * a.in_qs + in_line(lr.ii) + in_off0;
         const int bytes = lr.valid ? 16 : 0;
         if (!lr.valid) src = reinterpret_cast<const cpx*>(a.in);
 #pragma unroll
@@ -196,7 +229,7 @@ fft_pass_kernel(const PassParams a) {
             for (int i = 0; i < 16; i++) x[i] = cconj_if(sm[i * NT + tid], ld_conj);
         } else {
             LineRef lr = line_ref(a, tile * T + ell_in);
-            const long long base = lr.q * a.in_qs, loc0 = lr.ii * a.in_is + in_off0;
+            const long long base = lr.q * a.in_qs, loc0 = in_line(lr.ii) + in_off0;
 #pragma unroll
             for (int i = 0; i < PPT; i++) {
                 cpx v = make_double2(0.0, 0.0);
@@ -275,7 +308,7 @@ fft_pass_kernel(const PassParams a) {
 
         // ---- store
         if (lo.valid) {
-            const long long base = lo.q * a.out_qs, loc0 = lo.ii * a.out_is + out_off0;
+            const long long base = lo.q * a.out_qs, loc0 = out_line(lo.ii) + out_off0;
             double sx = 1.0, sy = 1.0;
             if (a.st_flags & ST_SCALE) { sx = a.scale; sy = a.scale; }
             if (a.st_flags & ST_CONJ) sy = -sy;
