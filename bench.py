@@ -49,6 +49,25 @@ def parse():
 
 
 # --------------------------------------------------------------------------- helpers
+def ncu_traffic(kernel_substr):
+    """dram read+write bytes per launch of a kernel, from the committed ncu --set full summary (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")
+    try:
+        with open(p) as f:
+            rows = [r for r in json.load(f) if kernel_substr in r.get("Kernel Name", "")]
+        vals = []
+        for r in rows:
+            tot = 0.0
+            for k, v in r.items():
+                if k.startswith("dram__bytes_read.sum") or k.startswith("dram__bytes_write.sum"):
+                    unit = k[k.index("[") + 1:k.index("]")]
+                    tot += float(v.replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+            vals.append(tot)
+        return (sum(vals) / len(vals)) if vals else None
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -289,7 +308,8 @@ def run_ours(args):
                    "parallelism": "batch rows sharded over %d GPU(s), no collective" % world},
         "roofline": {"bound": "hbm", "kernel": "gd::fft_pass_kernel<10,4,false> (both four-step passes are launches of this kernel)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src, "traffic": ncu_traffic("fft_pass_kernel"),
+                     "traffic_note": "dram read+write bytes per launch from profiles/r1_ncu_full_summary.json (ncu --set full, 64-transform chunk): the two-launch four-step writes and re-reads the intermediate, so HBM traffic is 2x the algorithmic bytes",
                      "algorithmic_bytes_per_launch": per_gpu_bytes / max(1.0, launches_per_step),
                      "avg_launch_us": ms * 1e3 / max(1.0, launches_per_step),
                      "note": "32 B/point (16 read + 16 written once, SURVEY.md 8d) x points per step / CUDA-event step time; each launch is one pass over one chunk and is charged half"},
@@ -386,7 +406,7 @@ def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_
                    "samples_per_gpu": ns_local, "segments_total": int(nsegs), "bins": lp,
                    "parallelism": "segment ranges sharded over %d GPU(s); one %d-double all-gather, summed in rank order" % (world, lp)},
         "roofline": {"bound": "hbm", "kernel": "gd::pwelch_fused_kernel<12>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": None,
+                     "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": ncu_traffic("pwelch_fused_kernel"),
                      "note": "8 B per input sample (SURVEY.md 8d); FP64 issue rate, not HBM, is the tighter roof for this kernel (DESIGN.md)"},
         "clocks": clocks, "_launches": int(launches),
         "pxx_checksum": float(pxx.sum().item()),

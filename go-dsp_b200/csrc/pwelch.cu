@@ -7,6 +7,8 @@
 // the SUM of periodograms is needed, |A[k]|^2 + |B[k]|^2 = (|Z[k]|^2 + |Z[L-k]|^2)/2 --
 // no per-segment separation. Each thread keeps 16 running sums (bins p + P*i) for its
 // whole share of segments; a deterministic fold adds the per-group partials.
+#include <stdint.h>
+
 #include "engine.h"
 #include "fft_pass.cuh"
 
@@ -20,7 +22,10 @@ struct PwShape {
     static constexpr int LS = line_stride(L, T);
 };
 
-template <int LOG2L>
+// PREFETCH: the samples of the next segment pair (one contiguous range of stride + nfft doubles: the two
+// segments overlap) are copied with cp.async into the group's idle exchange buffer while the last
+// butterfly step and the |Z|^2 accumulation of the current pair run; needs 16-byte aligned ranges.
+template <int LOG2L, bool PREFETCH>
 __global__ void __launch_bounds__(PwShape<LOG2L>::T * PwShape<LOG2L>::P, 2)
 pwelch_fused_kernel(const double* __restrict__ x, long long nfft, long long stride, long long seg0, long long nseg,
                     const double* __restrict__ win, double* __restrict__ partial, const cpx* __restrict__ wl) {
@@ -32,6 +37,7 @@ pwelch_fused_kernel(const double* __restrict__ x, long long nfft, long long stri
 
     const int tid = threadIdx.x, p = tid % P, ell = tid / P;
     cpx* sl = sm + ell * LS;
+    const double* stage = reinterpret_cast<const double*>(sl);
     const long long npairs = (nseg + 1) / 2;
     const long long GG = (long long)gridDim.x * T;
     const long long gg = (long long)blockIdx.x * T + ell;
@@ -44,45 +50,76 @@ pwelch_fused_kernel(const double* __restrict__ x, long long nfft, long long stri
         iters = c > iters ? c : iters;
     }
 
+    auto prefetch = [&](long long u) {             // this group's threads copy [xa, xa + count) into sl
+        if (u < u1) {
+            const double* xa = x + (seg0 + 2 * u) * stride;
+            const long long count = (2 * u + 1 < nseg) ? stride + nfft : nfft;
+            const long long n16 = count >> 1;
+            for (long long c = p; c < n16; c += P) cp_async16(sl + c, xa + 2 * c, 16);
+            if ((count & 1) && p == 0) {
+                unsigned s = (unsigned)__cvta_generic_to_shared(reinterpret_cast<double*>(sl) + count - 1);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(xa + count - 1) : "memory");
+            }
+        }
+        cp_async_commit();
+    };
+
     double acc[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) acc[i] = 0.0;
+    if constexpr (PREFETCH) prefetch(u0);
 
     for (long long it = 0; it < iters; it++) {
         const long long u = u0 + it;
         const bool act = u < u1;
         const bool has_b = act && (2 * u + 1 < nseg);
-        const double* xa = x + (seg0 + 2 * u) * stride;
-        const double* xb = xa + stride;
         cpx z[16];
+        if constexpr (PREFETCH) {
+            cp_async_wait_all();
+            __syncthreads();                      // the pair's samples (copied by all threads of the group) are visible
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const int n = p + P * i;
-            double a = 0.0, b = 0.0, w = 0.0;
-            if (act && n < nfft) {
-                w = __ldg(win + n);
-                a = __ldg(xa + n);
-                if (has_b) b = __ldg(xb + n);
+            for (int i = 0; i < 16; i++) {
+                const int n = p + P * i;
+                double a = 0.0, b = 0.0, w = 0.0;
+                if (act && n < nfft) {
+                    w = __ldg(win + n);
+                    a = stage[n];
+                    if (has_b) b = stage[stride + n];
+                }
+                z[i] = make_double2(w * a, w * b);
             }
-            z[i] = make_double2(w * a, w * b);
+        } else {
+            const double* xa = x + (seg0 + 2 * u) * stride;
+            const double* xb = xa + stride;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int n = p + P * i;
+                double a = 0.0, b = 0.0, w = 0.0;
+                if (act && n < nfft) {
+                    w = __ldg(win + n);
+                    a = __ldg(xa + n);
+                    if (has_b) b = __ldg(xb + n);
+                }
+                z[i] = make_double2(w * a, w * b);
+            }
         }
         butterfly_step<L, 16, 1>(z, p, wl);
+        if constexpr (PREFETCH) __syncthreads();  // all staged samples consumed before the scatter overwrites them
         scatter_step<L, 16, 1>(z, p, sl);
         __syncthreads();
         gather_step<L>(z, p, sl);
-        if constexpr (NSTEP == 2) {
-            butterfly_step<L, LASTR, 16>(z, p, wl);
-        } else {
+        if constexpr (NSTEP == 3) {
             __syncthreads();
             butterfly_step<L, 16, 16>(z, p, wl);
             scatter_step<L, 16, 16>(z, p, sl);
             __syncthreads();
             gather_step<L>(z, p, sl);
-            butterfly_step<L, LASTR, 256>(z, p, wl);
         }
+        __syncthreads();                          // exchange buffer idle again
+        if constexpr (PREFETCH) prefetch(u + 1);
+        butterfly_step<L, LASTR, (NSTEP == 2 ? 16 : 256)>(z, p, wl);
 #pragma unroll
         for (int i = 0; i < 16; i++) acc[i] = fma(z[i].x, z[i].x, fma(z[i].y, z[i].y, acc[i]));
-        __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) partial[gg * L + p + P * i] = acc[i];
@@ -133,9 +170,13 @@ template <int LOG2L>
 static Status launch_fused(Device& d, const double* x, long long nfft, long long stride, long long lp, long long seg0,
                            long long nseg, const double* win, double* raw, cudaStream_t st) {
     using SH = PwShape<LOG2L>;
-    auto kern = pwelch_fused_kernel<LOG2L>;
+    // the staged path needs every pair's sample range 16-byte aligned
+    // (pair u starts 2*u*stride doubles = 16*u*stride bytes after the first one)
+    const bool aligned = (reinterpret_cast<uintptr_t>(x + seg0 * stride) & 15) == 0;
+    auto kern = aligned ? pwelch_fused_kernel<LOG2L, true> : pwelch_fused_kernel<LOG2L, false>;
     const int threads = SH::T * SH::P, smem = SH::T * SH::LS * (int)sizeof(cpx);
-    static int blocks_per_sm = 0;
+    static int bps[2] = {0, 0};
+    int& blocks_per_sm = bps[aligned ? 1 : 0];
     if (!blocks_per_sm) {
         GD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int b = 0;
