@@ -371,6 +371,21 @@ int gd_fftn_c2c_dev(const double* in, double* out, const int64_t* dims, int nd, 
     GD_ENTER();
     return (int)fftn(d, (const cpx*)in, (cpx*)out, ld, nd, dir, pick(d, stream));
 }
+int gd_fourstep_twiddle_dev(double* blk, int64_t rows, int64_t cols, int64_t row0, int64_t col0, int log2n, void* stream) {
+    if (!blk) return (int)invalid_arg("fourstep_twiddle_dev: null");
+    GD_ENTER();
+    return (int)fourstep_twiddle((cpx*)blk, rows, cols, row0, col0, log2n, pick(d, stream));
+}
+int gd_repack_gkw_dev(const double* in, double* out, int64_t g, int64_t k, int64_t w, void* stream) {
+    if (!in || !out) return (int)invalid_arg("repack_gkw_dev: null");
+    GD_ENTER();
+    return (int)repack_gkw((const cpx*)in, (cpx*)out, g, k, w, pick(d, stream));
+}
+int gd_fft_strided_c2c_dev(const double* in, double* out, int64_t outer, int64_t len, int64_t stride, int dir, void* stream) {
+    if (!in || !out || (dir != 1 && dir != -1)) return (int)invalid_arg("fft_strided_dev: bad arguments");
+    GD_ENTER();
+    return (int)fft_strided(d, (const cpx*)in, (cpx*)out, outer, len, stride, dir, pick(d, stream));
+}
 int gd_pwelch_partial_dev(const double* x, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp, int64_t seg0,
                           int64_t nseg, const double* win, double* raw, void* stream) {
     if (!x || !win || !raw || noverlap < 0 || noverlap >= nfft) return (int)invalid_arg("pwelch_dev: bad arguments");

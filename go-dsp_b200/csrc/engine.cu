@@ -334,6 +334,51 @@ __global__ void splitmix_kernel(double* out, long long n, unsigned long long see
     for (; i < n; i += stride) out[i] = splitmix_unit(seed, offset + (unsigned long long)i);
 }
 
+// ---- distributed four-step helpers (config C5: one transform of N = N1*N2 points over G GPUs) ----
+// block[r][c] *= w_N^((row0 + r) * (col0 + c)), N = 2^log2n <= 2^40. One thread owns 16 consecutive c of a row:
+// base and step come from sincospi of exactly reduced exponents, the run by a 15-term product chain.
+__global__ void fourstep_twiddle_kernel(cpx* __restrict__ blk, long long rows, long long cols, long long row0,
+                                        long long col0, int log2n) {
+    const long long runs_per_row = (cols + 15) / 16;
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= rows * runs_per_row) return;
+    const long long r = t / runs_per_row, c = (t - r * runs_per_row) * 16;
+    const unsigned long long mask = (1ULL << log2n) - 1ULL, gr = (unsigned long long)(row0 + r);
+    const double invn = 1.0 / (double)(1ULL << log2n);
+    double s, co;
+    sincospi(-2.0 * (double)((gr * (unsigned long long)(col0 + c)) & mask) * invn, &s, &co);
+    cpx w = make_double2(co, s);
+    sincospi(-2.0 * (double)(gr & mask) * invn, &s, &co);
+    const cpx step = make_double2(co, s);
+    cpx* p = blk + r * cols + c;
+    const int n = (int)(cols - c < 16 ? cols - c : 16);
+    for (int i = 0; i < n; i++) { p[i] = cmul(p[i], w); w = cmul(w, step); }
+}
+// all-to-all receive buffer [G][K][W] (source rank, local row, source's column) -> rows [K][G*W]
+__global__ void repack_gkw_kernel(const cpx* __restrict__ in, cpx* __restrict__ out, long long G, long long K, long long W) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= G * K * W) return;
+    const long long j = t % W, k = (t / W) % K, g = t / (W * K);
+    out[k * (G * W) + g * W + j] = in[t];
+}
+
+Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st) {
+    if (rows < 1 || cols < 1 || log2n < 1 || log2n > 40) return invalid("fourstep_twiddle: bad arguments");
+    long long threads = rows * ((cols + 15) / 16);
+    fourstep_twiddle_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(blk, rows, cols, row0, col0, log2n);
+    g_launches++;
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+Status repack_gkw(const cpx* in, cpx* out, long long G, long long K, long long W, cudaStream_t st) {
+    if (G < 1 || K < 1 || W < 1 || in == out) return invalid("repack_gkw: bad arguments");
+    long long n = G * K * W;
+    repack_gkw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, G, K, W);
+    g_launches++;
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
 static inline unsigned grid_for(long long n, int block) {
     long long g = (n + block - 1) / block;
     return (unsigned)(g < 1 ? 1 : g);
@@ -517,6 +562,11 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         GD_CUDA(cudaGetLastError());
     }
     return GD_OK;
+}
+
+Status fft_strided(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st) {
+    if (outer < 1 || len < 1 || s < 1) return invalid("fft_strided: bad arguments");
+    return fft_axis(d, src, dst, outer, len, s, dir, st);
 }
 
 Status fftn(Device& d, const cpx* in, cpx* out, const long long* dims, int nd, int dir, cudaStream_t st) {

@@ -116,6 +116,12 @@ Status pwelch_partial(Device& d, const double* x, long long nfft, long long stri
 // pxx[j] = raw[j] / nsegs (x2 for 0<j<lp-1) / norm      (spectral/pwelch.go:113-121,134-136)
 Status pwelch_finalize(const double* raw, long long lp, long long nsegs, double norm, double* pxx, cudaStream_t st);
 
+// ---- distributed four-step (C5) building blocks -------------------------------------------
+Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st);
+Status repack_gkw(const cpx* in, cpx* out, long long G, long long K, long long W, cudaStream_t st);
+// strided lines: `outer` blocks of `len` lines-elements with element stride s (fft_axis)
+Status fft_strided(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st);
+
 // ---- utilities -----------------------------------------------------------------------------
 Status fill_splitmix(double* out, long long n, unsigned long long seed, unsigned long long offset, cudaStream_t st);
 

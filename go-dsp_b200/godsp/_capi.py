@@ -33,6 +33,9 @@ SIGNATURES = {
     "gd_fft_batch_r2c_full_dev": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
     "gd_convolve_c2c_dev": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "gd_fftn_c2c_dev": (_int, [_vp, _vp, C.POINTER(_i64), _int, _int, _vp]),
+    "gd_fft_strided_c2c_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "gd_fourstep_twiddle_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp]),
+    "gd_repack_gkw_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "gd_pwelch_partial_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "gd_pwelch_finalize_dev": (_int, [_vp, _i64, _i64, C.c_double, _vp, _vp]),
     "gd_kernel_launches": (_i64, []),

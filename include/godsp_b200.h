@@ -108,6 +108,13 @@ GD_API int gd_fft_batch_c2c_dev(const double* in_dev, double* out_dev, int64_t n
 GD_API int gd_fft_batch_r2c_full_dev(const double* in_dev, double* out_dev, int64_t n, int64_t batch, int dir, void* stream);
 GD_API int gd_convolve_c2c_dev(const double* x_dev, const double* y_dev, double* out_dev, int64_t n, void* stream);
 GD_API int gd_fftn_c2c_dev(const double* in_dev, double* out_dev, const int64_t* dims, int nd, int dir, void* stream);
+/* Lines of length len and element stride `stride` (stride adjacent lines per block, `outer` blocks): the FFTN axis
+ * primitive (fft/fft.go:175-189), exposed for the distributed four-step. in may equal out. */
+GD_API int gd_fft_strided_c2c_dev(const double* in_dev, double* out_dev, int64_t outer, int64_t len, int64_t stride, int dir, void* stream);
+/* Distributed four-step building blocks (BASELINE config 5: one 2^32-point transform over 8 GPUs):
+ * blk[r][c] *= w_N^((row0+r)*(col0+c)), N = 2^log2n;  and the all-to-all receive layout [G][K][W] -> rows [K][G*W]. */
+GD_API int gd_fourstep_twiddle_dev(double* blk_dev, int64_t rows, int64_t cols, int64_t row0, int64_t col0, int log2n, void* stream);
+GD_API int gd_repack_gkw_dev(const double* in_dev, double* out_dev, int64_t g, int64_t k, int64_t w, void* stream);
 /* raw[j] = sum over segments seg0..seg0+nseg-1 of |FFT(win * segment)[j]|^2, j < lp (one GPU's share) */
 GD_API int gd_pwelch_partial_dev(const double* x_dev, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
                           int64_t seg0, int64_t nseg, const double* win_dev, double* raw_dev, void* stream);
