@@ -145,6 +145,8 @@ int gd_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "pass_scratch_mb")) { if (value < 1) return (int)invalid_arg("pass_scratch_mb < 1"); d.pass_scratch_budget = (size_t)value << 20; }
     else if (!strcmp(key, "wide_tiles")) d.wide_tiles = value != 0;
     else if (!strcmp(key, "fused")) d.use_fused = value != 0;
+    else if (!strcmp(key, "debug_alias")) d.debug_alias = value != 0;
+    else if (!strcmp(key, "w32")) { if (value < 0 || value > 6) return (int)invalid_arg("w32 out of range"); d.w32 = (int)value; }
     else if (!strcmp(key, "tiled_scratch")) d.tiled_scratch = value != 0;
     else if (!strcmp(key, "l2_window")) d.use_l2_window = value != 0;
     else if (!strcmp(key, "fused_delay")) { if (value < 1 || value > 6) return (int)invalid_arg("fused_delay out of range"); d.fused_delay = (int)value; }

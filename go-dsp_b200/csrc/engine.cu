@@ -13,6 +13,8 @@ namespace gd {
 
 cudaError_t launch_fused(int log2l, bool wide, const FusedParams& a, long long total_items, int num_sms, cudaStream_t st);
 int fused_tile_lines(int log2l, bool wide);
+cudaError_t launch_pass32(int variant, const PassParams& a, int num_sms, cudaStream_t st);
+int pass32_tile_lines(int variant);
 
 // ------------------------------------------------------------------ errors
 std::atomic<long long> g_launches{0};
@@ -83,6 +85,7 @@ Status Device::init(int device) {
     if (const char* s = getenv("GD_WIDE_TILES")) wide_tiles = atoi(s) != 0;
     if (const char* s = getenv("GD_FUSED")) use_fused = atoi(s) != 0;
     if (const char* s = getenv("GD_TILED")) tiled_scratch = atoi(s) != 0;
+    if (const char* s = getenv("GD_W32")) w32 = atoi(s);
     if (const char* s = getenv("GD_L2_WINDOW")) use_l2_window = atoi(s) != 0;
     if (const char* s = getenv("GD_FUSED_DELAY")) { int v = atoi(s); if (v >= 1 && v <= 6) fused_delay = v; }
     if (getenv("GD_VERBOSE")) fprintf(stderr, "[godsp] dev %d: %d SMs, L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", dev, num_sms, prop.l2CacheSize >> 20, l2_persist_max >> 20, l2_window_max >> 20);
@@ -145,7 +148,8 @@ static Status launch_pass(Device& d, int log2l, const PassParams& p, cudaStream_
     bool generic = (p.ld_flags & (LD_REAL | LD_PAD | LD_MULAUX | LD_REVERSE)) ||
                    (p.st_flags & (ST_MULAUX | ST_DIV | ST_TRUNC));
     cudaError_t e;
-    if (log2l >= 1 && log2l <= 8) e = launch_pass_small(log2l, p, generic, d.num_sms, st);
+    if (log2l == 10 && !generic && d.w32 >= 1 && d.w32 <= 6) e = launch_pass32(d.w32, p, d.num_sms, st);   // 32 points per thread
+    else if (log2l >= 1 && log2l <= 8) e = launch_pass_small(log2l, p, generic, d.num_sms, st);
     else if (log2l <= 10) e = launch_pass_mid(log2l, d.wide_tiles, p, generic, d.num_sms, st);
     else if (log2l <= 12) e = launch_pass_big(log2l, d.wide_tiles, p, generic, d.num_sms, st);
     else return invalid("launch_pass: line length out of range");
@@ -238,6 +242,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         return GD_OK;
     }
     // four-step: N = N1 * N2, n = n1*N2 + n2, k = k1 + N1*k2
+    if (d.debug_alias) { in_dist = 0; out_dist = 0; }   // experiment: every transform on the same L2-resident buffers
     const int l1 = (log2n + 1) / 2, l2 = log2n - l1;
     const long long N1 = 1LL << l1, N2 = 1LL << l2;
     TwiddleTable tw;
@@ -252,14 +257,16 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         long long nb = batch - b0 < chunk ? batch - b0 : chunk;
         // pass 1: columns n2 of every transform, length N1, twiddle w_N^(n2*k1) on store; the intermediate
         // is tile-major (T adjacent columns = one contiguous block) so these stores are fully coalesced
-        const int T1 = pass_tile_lines(l1, d.wide_tiles), T2 = pass_tile_lines(l2, d.wide_tiles);
-        const bool tiled = d.tiled_scratch && T1 == T2 && ((N2 / 16) % T1) == 0 && !(ops.st_flags & ~(ST_CONJ | ST_SCALE)) ;
+        const bool lean32 = d.w32 >= 1 && d.w32 <= 6 && !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
+        const int T1 = (l1 == 10 && lean32) ? pass32_tile_lines(d.w32) : pass_tile_lines(l1, d.wide_tiles);
+        const int T2 = (l2 == 10 && lean32) ? pass32_tile_lines(d.w32) : pass_tile_lines(l2, d.wide_tiles);
+        const bool tiled = d.tiled_scratch && T1 == T2 && ((N2 / 32) % T1) == 0 && !(ops.st_flags & ~(ST_CONJ | ST_SCALE)) && !(ops.ld_flags & ~LD_CONJ);
         PassParams p = base_params(d, l1);
         p.in = real_in ? (const void*)((const double*)in + b0 * in_dist) : (const void*)((const cpx*)in + b0 * in_dist);
         p.out = scr;
         p.nlines = nb * N2; p.inner = N2;
         p.in_qs = in_dist; p.in_is = 1; p.in_es = (int)N2;
-        p.out_qs = N; p.out_is = 1; p.out_es = (int)N2;
+        p.out_qs = d.debug_alias ? 0 : N; p.out_is = 1; p.out_es = (int)N2;
         p.in_mode = p.out_mode = MODE_COL;
         p.ld_flags = ops.ld_flags; p.aux_in = ops.aux_in; p.n_valid_in = ops.n_valid_in;
         p.st_flags = ST_TWIDDLE; p.tw_sel = 0; p.tw_log2m = log2n; p.tw_lo = tw.lo; p.tw_hi = tw.hi;
@@ -269,7 +276,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         PassParams r = base_params(d, l2);
         r.in = scr; r.out = out + b0 * out_dist;
         r.nlines = nb * N1; r.inner = N1;
-        r.in_qs = N; r.in_is = N2; r.in_es = 1;
+        r.in_qs = d.debug_alias ? 0 : N; r.in_is = N2; r.in_es = 1;
         r.out_qs = out_dist; r.out_is = 1; r.out_es = (int)N1;
         r.in_mode = MODE_ROW; r.out_mode = MODE_COL;
         if (tiled) { r.in_tiled = 1; r.tiled_len = (int)N1; r.in_mode = MODE_COL; }

@@ -78,6 +78,8 @@ struct Device {
     size_t scratch_bytes[SCR_NSLOTS] = {0};
     size_t pass_scratch_budget = 1ull << 30;    // inter-pass scratch of the two-launch four-step path (chunk of transforms)
     bool wide_tiles = false;             // 512-thread tiles for L >= 1024
+    int w32 = 2;                         // 1024-point lean passes: 32 points per thread (fft_w32.cuh); 0 = 16-point kernel
+    bool debug_alias = false;            // timing experiment only: all transforms of a batch alias one buffer (results are garbage)
     bool tiled_scratch = false;          // tile-major four-step intermediate (measured slower: pass 2 loses its contiguous row reads)
     size_t l2_persist_max = 0;           // cudaDevAttrMaxPersistingL2CacheSize
     size_t l2_window_max = 0;            // cudaDevAttrMaxAccessPolicyWindowSize
