@@ -383,6 +383,11 @@ int gd_repack_gkw_dev(const double* in, double* out, int64_t g, int64_t k, int64
     GD_ENTER();
     return (int)repack_gkw((const cpx*)in, (cpx*)out, g, k, w, pick(d, stream));
 }
+int gd_transpose_batched_dev(const double* in, double* out, int64_t batch, int64_t rows, int64_t cols, void* stream) {
+    if (!in || !out) return (int)invalid_arg("transpose_batched_dev: null");
+    GD_ENTER();
+    return (int)transpose_batched((const cpx*)in, (cpx*)out, batch, rows, cols, pick(d, stream));
+}
 int gd_fft_strided_c2c_dev(const double* in, double* out, int64_t outer, int64_t len, int64_t stride, int dir, void* stream) {
     if (!in || !out || (dir != 1 && dir != -1)) return (int)invalid_arg("fft_strided_dev: bad arguments");
     GD_ENTER();

@@ -369,6 +369,39 @@ __global__ void repack_gkw_kernel(const cpx* __restrict__ in, cpx* __restrict__ 
     out[k * (G * W) + g * W + j] = in[t];
 }
 
+// batched transpose in[b][r][c] -> out[b][c][r] through a padded 32 x 32 shared-memory tile (both sides coalesced):
+// turns each source rank's [K][W] all-to-all block into [W][K], so the received slab is [N2][K] and the second
+// four-step pass runs as strided lines with its output already in natural order
+__global__ void __launch_bounds__(256) transpose_batched_kernel(const cpx* __restrict__ in, cpx* __restrict__ out,
+                                                                long long rows, long long cols) {
+    __shared__ cpx tile[32][33];
+    const long long b = blockIdx.z;
+    const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const cpx* src = in + b * rows * cols;
+    cpx* dst = out + b * rows * cols;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const long long r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + 8 * i][tx] = src[r * cols + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const long long c = c0 + ty + 8 * i, r = r0 + tx;
+        if (r < rows && c < cols) dst[c * rows + r] = tile[tx][ty + 8 * i];
+    }
+}
+Status transpose_batched(const cpx* in, cpx* out, long long batch, long long rows, long long cols, cudaStream_t st) {
+    if (batch < 1 || rows < 1 || cols < 1 || in == out) return invalid("transpose_batched: bad arguments");
+    const long long gx = (cols + 31) / 32, gy = (rows + 31) / 32;
+    if (gy > 65535 || batch > 65535) return invalid("transpose_batched: grid too large");
+    transpose_batched_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)batch), 256, 0, st>>>(in, out, rows, cols);
+    g_launches++;
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
 Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st) {
     if (rows < 1 || cols < 1 || log2n < 1 || log2n > 40) return invalid("fourstep_twiddle: bad arguments");
     long long threads = rows * ((cols + 15) / 16);

@@ -1,0 +1,140 @@
+"""The two paths of SURVEY.md 8(e) that need an exchange step, one process per GPU over torch.distributed:
+
+* `fft_1d_sharded` -- ONE transform of N = N1*N2 points over G ranks (BASELINE config 5: 2^32 points on
+  8 GPUs) as a four-step decomposition with a single all-to-all.  Index maps (same as the single-GPU
+  four-step in csrc/engine.cu, which replaces the log2 N sweeps of fft/radix2.go:131-151):
+      n = n1*N2 + n2,   k = k1 + N1*k2,
+      X[k1 + N1*k2] = sum_n2 w_N2^(n2 k2) * w_N^(n2 k1) * sum_n1 w_N1^(n1 k1) x[n1*N2 + n2].
+  Layout: the signal viewed as a row-major [N1][N2] matrix, rank g holds the column slab
+  [N1][g*W, (g+1)*W), W = N2/G; the spectrum viewed as a row-major [N2][N1] matrix, rank g holds the
+  column slab [N2][g*K, (g+1)*K), K = N1/G.  Input and output have the same kind of layout, so no extra
+  transposes are needed: strided length-N1 lines -> twiddle -> all-to-all -> per-source [K][W]->[W][K]
+  transpose -> strided length-N2 lines.  `scatter_signal` / `gather_spectrum` give the maps from/to natural order.
+
+* `fft2_sharded` -- fft.FFT2 (fft/fft.go:123-154: every column, then every row) on a matrix whose row
+  blocks are spread over the ranks; columns become local through one all-to-all, and a second one
+  restores the row-block layout.
+
+The arithmetic is done by an `ops` object.  `DeviceOps` is the product: every method is one call into
+the C ABI (include/godsp_b200.h) on CUDA tensors, and raises if the library or the GPU is missing.
+The CPU test suite passes its own stand-in (tests/test_multi_rank_cpu.py) to check the data movement
+under gloo; nothing in this module computes on the host.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _capi
+
+
+def _ilog2(n):
+    lg = n.bit_length() - 1
+    if n < 1 or (1 << lg) != n:
+        raise ValueError("power of two expected, got %d" % n)
+    return lg
+
+
+class DeviceOps:
+    """C-ABI-backed building blocks; tensors are 1-D complex128 CUDA tensors."""
+
+    def __init__(self, device=None, stream=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("go-dsp_b200: no CUDA device; there is no CPU fallback")
+        self.L = _capi.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        _capi.check(self.L.gd_use_device(self.device.index or 0))
+        self.stream = stream
+
+    def _sp(self):
+        s = self.stream if self.stream is not None else torch.cuda.current_stream(self.device)
+        return C.c_void_p(s.cuda_stream)
+
+    def empty(self, nelem):
+        return torch.empty(nelem, dtype=torch.complex128, device=self.device)
+
+    def fft_strided(self, src, dst, outer, length, stride, direction=1):
+        _capi.check(self.L.gd_fft_strided_c2c_dev(src.data_ptr(), dst.data_ptr(), outer, length, stride, direction, self._sp()))
+
+    def fft_rows(self, src, dst, n, batch, direction=1):
+        _capi.check(self.L.gd_fft_batch_c2c_dev(src.data_ptr(), dst.data_ptr(), n, batch, direction, self._sp()))
+
+    def fourstep_twiddle(self, blk, rows, cols, row0, col0, log2n):
+        _capi.check(self.L.gd_fourstep_twiddle_dev(blk.data_ptr(), rows, cols, row0, col0, log2n, self._sp()))
+
+    def swap_leading(self, src, dst, a, b, w):
+        """src[a][b][w] -> dst[b][a][w]"""
+        _capi.check(self.L.gd_repack_gkw_dev(src.data_ptr(), dst.data_ptr(), a, b, w, self._sp()))
+
+    def transpose_batched(self, src, dst, batch, rows, cols):
+        """src[batch][rows][cols] -> dst[batch][cols][rows]"""
+        _capi.check(self.L.gd_transpose_batched_dev(src.data_ptr(), dst.data_ptr(), batch, rows, cols, self._sp()))
+
+
+def _all_to_all(recv, send, group):
+    # equal contiguous splits; complex128 travels as pairs of float64
+    dist.all_to_all_single(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), group=group)
+
+
+def split_1d(n, world):
+    """(N1, N2, K, W) of the sharded four-step: N = N1*N2, K = N1/world rows and W = N2/world columns per rank."""
+    lg = _ilog2(n)
+    l1 = (lg + 1) // 2
+    n1, n2 = 1 << l1, 1 << (lg - l1)
+    if n1 % world or n2 % world:
+        raise ValueError("world size %d must divide both factors %d x %d" % (world, n1, n2))
+    return n1, n2, n1 // world, n2 // world
+
+
+def fft_1d_sharded(slab, n, ops, group=None, work=None):
+    """Forward transform of one n-point signal.  `slab`: this rank's [N1][W] column slab (flattened, overwritten).
+    Returns this rank's [N2][K] slab of the spectrum (a new tensor, or `work` if given: n/world elements)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n1, n2, k, w = split_1d(n, world)
+    if slab.numel() != n1 * w:
+        raise ValueError("slab has %d elements, expected %d" % (slab.numel(), n1 * w))
+    recv = work if work is not None else ops.empty(n1 * w)
+    # 1. lines over n1 (length N1, element stride W), in place
+    ops.fft_strided(slab, slab, 1, n1, w, 1)
+    # 2. slab[k1][c] *= w_N^(k1 * (rank*W + c))
+    ops.fourstep_twiddle(slab, n1, w, 0, rank * w, _ilog2(n))
+    # 3. rows [h*K, (h+1)*K) go to rank h; received: [source g][K][W]
+    _all_to_all(recv, slab, group)
+    # 4. per source [K][W] -> [W][K]: the buffer becomes [N2][K] (n2 = g*W + c)
+    ops.transpose_batched(recv, slab, world, k, w)
+    # 5. lines over n2 (length N2, element stride K): out[k2][k1_local]
+    ops.fft_strided(slab, recv, 1, n2, k, 1)
+    return recv
+
+
+def scatter_signal(x, n, rank, world):
+    """Rank's [N1][W] slab of a natural-order signal (torch tensor, any device), flattened copy."""
+    n1, n2, _, w = split_1d(n, world)
+    return x.view(n1, n2)[:, rank * w:(rank + 1) * w].contiguous().view(-1)
+
+
+def gather_spectrum(slabs, n):
+    """Natural-order spectrum from the per-rank [N2][K] slabs (list in rank order)."""
+    world = len(slabs)
+    n1, n2, k, _ = split_1d(n, world)
+    return torch.cat([s.view(n2, k) for s in slabs], dim=1).contiguous().view(-1)
+
+
+def fft2_sharded(block, rows, cols, ops, group=None, direction=1):
+    """fft.FFT2 / IFFT2 of a rows x cols matrix; `block` is this rank's [rows/world][cols] row block
+    (flattened complex128, overwritten).  Returns the rank's row block of the result."""
+    world = dist.get_world_size(group)
+    if rows % world or cols % world:
+        raise ValueError("world size %d must divide %d x %d" % (world, rows, cols))
+    rg, wc = rows // world, cols // world
+    if block.numel() != rg * cols:
+        raise ValueError("block has %d elements, expected %d" % (block.numel(), rg * cols))
+    tmp = ops.empty(rg * cols)
+    # [rg][world][wc] -> [world][rg][wc]: destination-major send buffer
+    ops.swap_leading(block, tmp, rg, world, wc)
+    _all_to_all(block, tmp, group)                 # received [source][rg][wc] = [rows][wc]: my column slab
+    ops.fft_strided(block, block, 1, rows, wc, direction)      # every column (fft/fft.go:138-144)
+    _all_to_all(tmp, block, group)                 # rows [h*rg, (h+1)*rg) back to rank h: [source][rg][wc]
+    ops.swap_leading(tmp, block, world, rg, wc)    # -> [rg][cols]
+    ops.fft_rows(block, tmp, cols, rg, direction)  # every row (fft/fft.go:146-151)
+    return tmp

@@ -115,6 +115,8 @@ GD_API int gd_fft_strided_c2c_dev(const double* in_dev, double* out_dev, int64_t
  * blk[r][c] *= w_N^((row0+r)*(col0+c)), N = 2^log2n;  and the all-to-all receive layout [G][K][W] -> rows [K][G*W]. */
 GD_API int gd_fourstep_twiddle_dev(double* blk_dev, int64_t rows, int64_t cols, int64_t row0, int64_t col0, int log2n, void* stream);
 GD_API int gd_repack_gkw_dev(const double* in_dev, double* out_dev, int64_t g, int64_t k, int64_t w, void* stream);
+/* in[batch][rows][cols] -> out[batch][cols][rows] (complex128): per-source-rank transpose of the all-to-all receive buffer */
+GD_API int gd_transpose_batched_dev(const double* in_dev, double* out_dev, int64_t batch, int64_t rows, int64_t cols, void* stream);
 /* raw[j] = sum over segments seg0..seg0+nseg-1 of |FFT(win * segment)[j]|^2, j < lp (one GPU's share) */
 GD_API int gd_pwelch_partial_dev(const double* x_dev, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
                           int64_t seg0, int64_t nseg, const double* win_dev, double* raw_dev, void* stream);

@@ -1,0 +1,83 @@
+"""GPU tests of the exchange paths (godsp.distributed) through the C ABI: world size 1 on one GPU
+(every building-block kernel: strided lines, four-step twiddle, batched transpose, repack) against
+the CPU oracle, and -- when the box has two GPUs -- two NCCL ranks against the same oracle result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, log2n, rows, cols, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "go-dsp_b200"))
+    import torch
+    import torch.distributed as dist
+    from godsp import distributed as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ops = D.DeviceOps()
+    n = 1 << log2n
+    x = torch.from_numpy(oracle.splitmix_complex(n, 6))
+    slab = D.scatter_signal(x, n, rank, world).cuda()
+    spec = D.fft_1d_sharded(slab, n, ops)
+    torch.cuda.synchronize()
+    m = oracle.splitmix_complex(rows * cols, 4).reshape(rows, cols)
+    rg = rows // world
+    blk = torch.from_numpy(m[rank * rg:(rank + 1) * rg].copy().reshape(-1)).cuda()
+    res = D.fft2_sharded(blk, rows, cols, ops)
+    back = D.fft2_sharded(res.clone(), rows, cols, ops, direction=-1)
+    torch.cuda.synchronize()
+    out[rank] = (spec.cpu().numpy(), res.cpu().numpy(), back.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(world, log2n, rows, cols):
+    import torch
+    import torch.multiprocessing as mp
+    from godsp import distributed as D
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), log2n, rows, cols, out), nprocs=world, join=True)
+    n = 1 << log2n
+    spec = D.gather_spectrum([torch.from_numpy(out[r][0]) for r in range(world)], n).numpy()
+    assert rel_l2(spec, oracle.fft(oracle.splitmix_complex(n, 6))) <= TOL
+    m = oracle.splitmix_complex(rows * cols, 4).reshape(rows, cols)
+    got = np.concatenate([out[r][1] for r in range(world)]).reshape(rows, cols)
+    assert rel_l2(got, oracle.fft2(m)) <= TOL
+    back = np.concatenate([out[r][2] for r in range(world)]).reshape(rows, cols)
+    assert rel_l2(back, m) <= TOL
+
+
+@pytest.mark.parametrize("log2n,rows,cols", [(12, 8, 16), (20, 512, 1024), (23, 8192, 64)])
+def test_sharded_paths_one_rank(log2n, rows, cols):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: these tests must run on the GPU box (there is no CPU fallback)")
+    _run(1, log2n, rows, cols)
+
+
+@pytest.mark.parametrize("log2n,rows,cols", [(12, 8, 16), (22, 2048, 512)])
+def test_sharded_paths_two_ranks(log2n, rows, cols):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: these tests must run on the GPU box (there is no CPU fallback)")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible; the 2-rank NCCL run needs `gpurun --gpus 2`")
+    _run(2, log2n, rows, cols)

@@ -69,3 +69,100 @@ def test_world2_matches_single_rank():
     pxx /= np.sum(win ** 2)
     want, _ = oracle.pwelch(x, 1.0, nfft=NFFT, noverlap=NOV)
     assert np.linalg.norm(pxx - want) / np.linalg.norm(want) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------
+# the two exchange paths (godsp.distributed): one sharded 1-D transform (four-step, one all-to-all)
+# and FFT2 on row blocks (two all-to-alls).  The ORACLE stands in for the device kernels; what is
+# checked here is the data movement: slab layouts, all-to-all splits, twiddle offsets, repacks.
+class OracleOps:
+    def empty(self, nelem):
+        return torch.empty(nelem, dtype=torch.complex128)
+
+    @staticmethod
+    def _fft(line, direction):
+        return oracle.fft(line) if direction > 0 else oracle.ifft(line)
+
+    def fft_strided(self, src, dst, outer, length, stride, direction=1):
+        a = src.numpy().reshape(outer, length, stride).copy()
+        for o in range(outer):
+            for c in range(stride):
+                a[o, :, c] = self._fft(np.ascontiguousarray(a[o, :, c]), direction)
+        dst.copy_(torch.from_numpy(a.reshape(-1)))
+
+    def fft_rows(self, src, dst, n, batch, direction=1):
+        a = src.numpy().reshape(batch, n)
+        dst.copy_(torch.from_numpy(np.stack([self._fft(np.ascontiguousarray(r), direction) for r in a]).reshape(-1)))
+
+    def fourstep_twiddle(self, blk, rows, cols, row0, col0, log2n):
+        r = np.arange(row0, row0 + rows, dtype=np.int64)[:, None]
+        c = np.arange(col0, col0 + cols, dtype=np.int64)[None, :]
+        e = (r * c) % (1 << log2n)
+        blk.copy_(torch.from_numpy((blk.numpy().reshape(rows, cols) * np.exp(-2j * np.pi * e / (1 << log2n))).reshape(-1)))
+
+    def swap_leading(self, src, dst, a, b, w):
+        dst.copy_(torch.from_numpy(np.ascontiguousarray(src.numpy().reshape(a, b, w).transpose(1, 0, 2)).reshape(-1)))
+
+    def transpose_batched(self, src, dst, batch, rows, cols):
+        dst.copy_(torch.from_numpy(np.ascontiguousarray(src.numpy().reshape(batch, rows, cols).transpose(0, 2, 1)).reshape(-1)))
+
+
+N1D, R2D, C2D = 1 << 10, 8, 16
+
+
+def _worker_exchange(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "go-dsp_b200"))
+    from godsp import distributed as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ops = OracleOps()
+    x = torch.from_numpy(oracle.splitmix_complex(N1D, 6))
+    slab = D.scatter_signal(x, N1D, rank, world)
+    spec = D.fft_1d_sharded(slab, N1D, ops)
+    got = [None] * world
+    dist.all_gather_object(got, spec.numpy())
+    m = oracle.splitmix_complex(R2D * C2D, 4).reshape(R2D, C2D)
+    rg = R2D // world
+    blk = torch.from_numpy(m[rank * rg:(rank + 1) * rg].copy().reshape(-1))
+    res = D.fft2_sharded(blk, R2D, C2D, ops)
+    back = D.fft2_sharded(res.clone(), R2D, C2D, ops, direction=-1)
+    got2 = [None] * world
+    dist.all_gather_object(got2, (res.numpy(), back.numpy()))
+    if rank == 0:
+        out["spec"] = D.gather_spectrum([torch.from_numpy(g) for g in got], N1D).numpy()
+        out["fft2"] = np.concatenate([g[0] for g in got2]).reshape(R2D, C2D)
+        out["ifft2"] = np.concatenate([g[1] for g in got2]).reshape(R2D, C2D)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_exchange_paths():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_exchange, args=(2, port, out), nprocs=2, join=True)
+
+    def rel(a, b):
+        return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+    want = oracle.fft(oracle.splitmix_complex(N1D, 6))
+    assert rel(out["spec"], want) < 1e-13
+    m = oracle.splitmix_complex(R2D * C2D, 4).reshape(R2D, C2D)
+    want2 = oracle.fft2(m)
+    assert rel(out["fft2"], want2) < 1e-13
+    assert rel(out["ifft2"], m) < 1e-13
+
+
+def test_split_1d_shapes():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "go-dsp_b200"))
+    from godsp import distributed as D
+    assert D.split_1d(1 << 32, 8) == (1 << 16, 1 << 16, 1 << 13, 1 << 13)      # BASELINE config 5
+    assert D.split_1d(1 << 21, 2) == (1 << 11, 1 << 10, 1 << 10, 1 << 9)
+    with pytest.raises(ValueError):
+        D.split_1d(1000, 2)
+    with pytest.raises(ValueError):
+        D.split_1d(1 << 4, 8)
