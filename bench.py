@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--pw-log2-samples", type=int, default=30, help="Pwelch samples per GPU per step (log2)")
     ap.add_argument("--e2e-batch", type=int, default=256, help="transforms per GPU in the host-buffer (e2e) run")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--skip", default="", help="comma list: pwelch,e2e,cpu")
+    ap.add_argument("--skip", default="", help="comma list: pwelch,e2e,cpu,extra")
     ap.add_argument("--scratch-mb", type=int, default=0, help="override the inter-pass scratch budget")
     ap.add_argument("--wide-tiles", type=int, default=-1)
     ap.add_argument("--fused", type=int, default=-1)
@@ -356,14 +356,87 @@ def run_ours(args):
         line["pwelch"] = run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_host, skip, hbm_peak, peak_src)
         line["gpu_launches"] += line["pwelch"].pop("_launches")
 
+    # ---------------- the other configs of BASELINE.json that shard with an exchange step
+    if "extra" not in skip:
+        line["fft2"] = run_fft2(args, torch, dist, L, sp, world, rank, timed, hbm_peak)
+        line["gpu_launches"] += line["fft2"].pop("_launches")
+        if world > 1:
+            line["fft_1d_sharded"] = run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed)
+            line["gpu_launches"] += line["fft_1d_sharded"].pop("_launches")
+
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def run_fft2(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
+    """fft.FFT2 on a 16384 x 16384 matrix (BASELINE.json configs[2]); N > 1: row blocks sharded, strong scaling."""
+    from godsp import _capi as capi
+    from godsp import distributed as D
+    R = Cc = 16384
+    rg = R // world
+    src = torch.empty(rg * Cc, dtype=torch.complex128, device="cuda")
+    capi.check(L.gd_fill_splitmix_dev(src.data_ptr(), 2 * rg * Cc, 4, 2 * rank * rg * Cc, sp))
+    steps, warmup = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
+    if world == 1:
+        out = torch.empty_like(blk)
+        dims = (C.c_int64 * 2)(R, Cc)
+
+        def step():
+            capi.check(L.gd_fftn_c2c_dev(src.data_ptr(), out.data_ptr(), dims, 2, 1, sp))
+        api = "gd_fftn_c2c_dev (columns then rows, fft/fft.go:138-151)"
+    else:
+        ops = D.DeviceOps()
+        blk = torch.empty(rg * Cc, dtype=torch.complex128, device="cuda")
+
+        def step():
+            blk.copy_(src)
+            D.fft2_sharded(blk, R, Cc, ops)
+        api = "godsp.distributed.fft2_sharded: repack, all-to-all, column lines, all-to-all, repack, row lines (+ one device copy of the input block per step)"
+    ms, launches, clocks = timed(step, steps, warmup)
+    return {"metric": "FFT2 Gelem/s (complex128, 16384 x 16384)", "value": R * Cc / (ms * 1e-3) / 1e9, "unit": "Gelem/s",
+            "ms_per_step": ms, "scaling": "strong", "api": api,
+            "roofline": {"bound": "hbm", "achieved": 64.0 * R * Cc / world / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": 64.0 * R * Cc / world / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "note": "64 B per element algorithmic: two sweeps, the 4 GiB matrix is far larger than L2 (SURVEY.md 8d)"},
+            "clocks": clocks, "_launches": int(launches)}
+
+
+def run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed):
+    """ONE transform of 2^29 points per GPU (2^32 at 8 GPUs = BASELINE.json configs[4]): four-step, one all-to-all."""
+    from godsp import _capi as capi
+    from godsp import distributed as D
+    lg = 29 + (world.bit_length() - 1)
+    if (1 << (world.bit_length() - 1)) != world:
+        return {"skipped": "world size %d is not a power of two" % world, "_launches": 0}
+    n = 1 << lg
+    n1, n2, k, w = D.split_1d(n, world)
+    ops = D.DeviceOps()
+    slab = torch.empty(n1 * w, dtype=torch.complex128, device="cuda")
+    src = torch.empty(n1 * w, dtype=torch.complex128, device="cuda")
+    work = torch.empty(n1 * w, dtype=torch.complex128, device="cuda")
+    # a synthetic slab (the layout is [N1][W]; values are SplitMix64 seed 6 at this rank's offset)
+    capi.check(L.gd_fill_splitmix_dev(src.data_ptr(), 2 * n1 * w, 6, 2 * rank * n1 * w, sp))
+    steps, warmup = max(2, min(args.steps, 3)), max(1, min(args.warmup, 2))
+
+    def step():
+        slab.copy_(src)
+        D.fft_1d_sharded(slab, n, ops, work=work)
+    ms, launches, clocks = timed(step, steps, warmup)
+    # Parseval on the last step: sum |X|^2 = n * sum |x|^2 over all ranks
+    e = torch.stack([(work.real ** 2 + work.imag ** 2).sum(), (src.real ** 2 + src.imag ** 2).sum()])
+    dist.all_reduce(e)
+    return {"metric": "single 1-D FFT GS/s (complex128, 2^%d points over %d GPUs)" % (lg, world), "value": n / (ms * 1e-3) / 1e9,
+            "unit": "GS/s", "ms_per_step": ms, "scaling": "weak", "log2n": lg,
+            "api": "godsp.distributed.fft_1d_sharded: strided lines, twiddle, NCCL all-to-all, transpose, strided lines (+ one device copy of the slab per step)",
+            "all_to_all_bytes_per_gpu": 16 * (n // world) * (world - 1) // world,
+            "parseval_rel_err": abs(float(e[0].item()) / (n * float(e[1].item())) - 1.0),
+            "clocks": clocks, "_launches": int(launches)}
+
+
 def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_host, skip, hbm_peak, peak_src):
-    import oracle  # window table + norm only (host-side O(NFFT) work the Go shim does); not on the timed path
+    from godsp import window as gwindow     # host-side mirror of window/window.go (what the Go shim evaluates)
     nfft, nov = PW_NFFT, PW_NOVERLAP
     stride = nfft - nov
     ns_local = 1 << args.pw_log2_samples                   # samples owned by this rank
@@ -377,7 +450,7 @@ def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_
     nloc = ns_local + halo
     x = torch.empty(nloc, dtype=torch.float64, device="cuda")
     capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), nloc, PW_SEED, rank * ns_local, sp))
-    win = oracle.window("hann", nfft)
+    win = gwindow.Hann(nfft)
     norm = 0.0
     for v in win:
         norm += v * v                                       # spectral/pwelch.go:124-128 (Fs = 1)

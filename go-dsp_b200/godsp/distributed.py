@@ -48,7 +48,9 @@ class DeviceOps:
 
     def _sp(self):
         s = self.stream if self.stream is not None else torch.cuda.current_stream(self.device)
-        return C.c_void_p(s.cuda_stream)
+        # torch's default stream is CUDA's legacy default stream (handle 0); the C ABI reads NULL as "the library's
+        # own stream", which would not be ordered with the collectives, so name the legacy stream explicitly
+        return C.c_void_p(s.cuda_stream if s.cuda_stream else 1)          # 1 = cudaStreamLegacy
 
     def empty(self, nelem):
         return torch.empty(nelem, dtype=torch.complex128, device=self.device)
