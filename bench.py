@@ -380,7 +380,7 @@ def run_fft2(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
     capi.check(L.gd_fill_splitmix_dev(src.data_ptr(), 2 * rg * Cc, 4, 2 * rank * rg * Cc, sp))
     steps, warmup = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
     if world == 1:
-        out = torch.empty_like(blk)
+        out = torch.empty_like(src)
         dims = (C.c_int64 * 2)(R, Cc)
 
         def step():

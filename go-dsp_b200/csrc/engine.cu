@@ -14,6 +14,9 @@ namespace gd {
 cudaError_t launch_fused(int log2l, bool wide, const FusedParams& a, long long total_items, int num_sms, cudaStream_t st);
 int fused_tile_lines(int log2l, bool wide);
 cudaError_t launch_pass32(int variant, const PassParams& a, int num_sms, cudaStream_t st);
+bool tma_fused_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist);
+Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long batch, int ld_conj,
+                    int st_conj, double scale, cudaStream_t st);
 int pass32_tile_lines(int variant);
 
 // ------------------------------------------------------------------ errors
@@ -86,6 +89,7 @@ Status Device::init(int device) {
     if (const char* s = getenv("GD_FUSED")) use_fused = atoi(s) != 0;
     if (const char* s = getenv("GD_TILED")) tiled_scratch = atoi(s) != 0;
     if (const char* s = getenv("GD_W32")) w32 = atoi(s);
+    if (const char* s = getenv("GD_TMA")) use_tma = atoi(s) != 0;
     if (const char* s = getenv("GD_L2_WINDOW")) use_l2_window = atoi(s) != 0;
     if (const char* s = getenv("GD_FUSED_DELAY")) { int v = atoi(s); if (v >= 1 && v <= 6) fused_delay = v; }
     if (getenv("GD_VERBOSE")) fprintf(stderr, "[godsp] dev %d: %d SMs, L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", dev, num_sms, prop.l2CacheSize >> 20, l2_persist_max >> 20, l2_window_max >> 20);
@@ -124,6 +128,16 @@ Status Device::ensure_scratch(ScratchSlot s, size_t bytes, void** out) {
     return GD_OK;
 }
 
+Status Device::l2_release() {
+    if (l2_dirty) {
+        GD_CUDA(cudaCtxResetPersistingL2Cache());
+        GD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+        l2_carved = 0;
+        l2_dirty = false;
+    }
+    return GD_OK;
+}
+
 Status Device::twiddles(int log2m, TwiddleTable* out) {
     auto it = tw.find(log2m);
     if (it == tw.end()) {
@@ -147,6 +161,7 @@ Status Device::twiddles(int log2m, TwiddleTable* out) {
 static Status launch_pass(Device& d, int log2l, const PassParams& p, cudaStream_t st) {
     bool generic = (p.ld_flags & (LD_REAL | LD_PAD | LD_MULAUX | LD_REVERSE)) ||
                    (p.st_flags & (ST_MULAUX | ST_DIV | ST_TRUNC));
+    GD_TRY(d.l2_release());
     cudaError_t e;
     if (log2l == 10 && !generic && d.w32 >= 1 && d.w32 <= 6) e = launch_pass32(d.w32, p, d.num_sms, st);   // 32 points per thread
     else if (log2l >= 1 && log2l <= 8) e = launch_pass_small(log2l, p, generic, d.num_sms, st);
@@ -186,6 +201,9 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
     }
     if (log2n > 24) return invalid("fft_pow2: N > 2^24 needs the multi-GPU path");
     const bool lean = !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
+    if (d.use_tma && lean && log2n == 20 && !d.debug_alias && tma_fused_applicable(in, in_dist, out, out_dist))
+        return fft_tma_2p20(d, (const cpx*)in, in_dist, out, out_dist, batch, (ops.ld_flags & LD_CONJ) ? 1 : 0,
+                            (ops.st_flags & ST_CONJ) ? 1 : 0, (ops.st_flags & ST_SCALE) ? ops.scale : 1.0, st);
     if (d.use_fused && lean && (log2n % 2) == 0 && log2n >= 16 && batch * (2LL << (log2n / 2)) < (1LL << 30)) {
         // both passes in one persistent kernel, intermediate resident in L2 (fft_fused.cuh)
         const int l = log2n / 2, T = fused_tile_lines(l, d.wide_tiles), tpt = (1 << l) / T;
@@ -232,6 +250,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             GD_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
         }
+        d.l2_dirty = window;
         cudaError_t e = launch_fused(l, d.wide_tiles, f, total_items, d.num_sms, st);
         if (window) {
             attr.accessPolicyWindow.num_bytes = 0;

@@ -62,7 +62,7 @@ struct BluesteinPlan {      // fft/bluestein.go:26-65 cache, plus the cached FFT
     cpx* bhat = nullptr;        // FFT_la(b), la entries
 };
 
-enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OUT, SCR_PWELCH, SCR_AUX, SCR_CNT, SCR_NSLOTS };
+enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OUT, SCR_PWELCH, SCR_AUX, SCR_CNT, SCR_TMA, SCR_NSLOTS };
 
 struct Device {
     int dev = -1;
@@ -85,14 +85,19 @@ struct Device {
     size_t l2_window_max = 0;            // cudaDevAttrMaxAccessPolicyWindowSize
     bool use_l2_window = true;
     size_t l2_carved = 0;                // current cudaLimitPersistingL2CacheSize on this device
+    bool l2_dirty = false;               // persisting lines / set-aside left behind by a fused launch
     int fused_delay = 2;                 // phases between P1(g) and P2(g) in the fused schedule
     bool use_fused = false;              // one persistent kernel for both four-step passes (N = L*L), L2-resident scratch
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
+    bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)
+    int tma_delay = 1;                   // phases between P1(g) and P2(g); delay + 2 slots of 16 MiB must stay in L2
     std::recursive_mutex mu;             // every public entry point locks its device
 
     Status init(int device);
     void destroy();
     Status ensure_scratch(ScratchSlot s, size_t bytes, void** out);
+    // give the whole L2 back to kernels that do not use the persisting window (called lazily by their launchers)
+    Status l2_release();
     Status twiddles(int log2m, TwiddleTable* out);
     Status bluestein(long long n, cudaStream_t st, const BluesteinPlan** out);
 };

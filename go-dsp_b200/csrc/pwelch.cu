@@ -207,6 +207,7 @@ Status pwelch_partial(Device& d, const double* x, long long nfft, long long stri
         set_error("pwelch: bad arguments");
         return GD_ERR_INVALID;
     }
+    GD_TRY(d.l2_release());
     if (nseg == 0) {
         GD_CUDA(cudaMemsetAsync(raw, 0, (size_t)lp * sizeof(double), st));
         return GD_OK;
