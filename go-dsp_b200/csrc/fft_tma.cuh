@@ -257,6 +257,7 @@ struct TmaFusedParams {
     int* queue;                  // next item of the sequence (zeroed by the host)
     int dbg_nodeps;              // timing experiments only: ignore the global dependencies (results are garbage)
     int dbg_nop1st;              // timing experiments only: skip the pass-1 stores
+    int dbg_nop2st, dbg_noload;  // timing experiments only: skip the pass-2 tile stores / the tile loads
     const cpx* wl;
     const cpx* tw_lo;
     const cpx* tw_hi;
@@ -603,6 +604,272 @@ fft_tma_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
     }
     if (a.stats && tig == 0) a.stats[blockIdx.x * 8 + 5 + g] = c_full;
+}
+
+
+// =====================================================================================================
+// Second fused kernel: landing slots decoupled from the work buffers.
+//
+// In fft_tma_fused_kernel a tile occupies one of three 64 KiB buffers from the moment its load is issued until
+// its outputs have drained (P2), so at most one tile is ever in flight per CTA and the consumers wait for data
+// about a quarter of the time (ncu: the `full` wait is the top stall). Here a tile lands in HALVES (512 rows =
+// two TMA boxes) in a ring of three 32 KiB slots and is copied to registers at once -- a slot is busy only
+// from issue to landing -- while the exchange and the P2 output staging use a 64 KiB work buffer owned by the
+// consumer group. The loader can therefore run a whole tile time ahead of each group.
+//   landing   3 x 32 KiB      full_h[s] (1 + tx), freed_h[s] (128)
+//   work      2 x 64 KiB      rd[g] (128): gathers done;  staged[g] (128): P2 outputs staged;  drained[g] (1): read out
+//   log[32] item ids by local step, log_count (monotonic, written by the loader) for the helper warps
+constexpr int TMA2_HALF_BYTES = TMA_TILE_BYTES / 2;          // 32768
+constexpr int TMA2_NSLOT = 3;
+constexpr int TMA2_SMEM = TMA2_NSLOT * TMA2_HALF_BYTES + 2 * TMA_TILE_BYTES + 1024;   // 230400
+
+__device__ __forceinline__ int ld_volatile_shared(const volatile int* p) { return *p; }
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_int,
+                      const __grid_constant__ CUtensorMap tm_out, const TmaFusedParams a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    cpx* land = reinterpret_cast<cpx*>(smem_raw);
+    cpx* work = reinterpret_cast<cpx*>(smem_raw + TMA2_NSLOT * TMA2_HALF_BYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + TMA2_NSLOT * TMA2_HALF_BYTES + 2 * TMA_TILE_BYTES);
+    unsigned long long* full_h = bars;                     // [3]
+    unsigned long long* freed_h = bars + 3;                // [3]
+    unsigned long long* rd = bars + 6;                     // [2]
+    unsigned long long* staged = bars + 8;                 // [2]
+    unsigned long long* drained = bars + 10;               // [2]
+    unsigned long long* pd = bars + 12;                    // [2][2]
+    volatile int* log = reinterpret_cast<volatile int*>(bars + 16);        // [32]
+    volatile int* log_count = reinterpret_cast<volatile int*>(bars + 32);  // local steps published by the loader
+    constexpr int TPT = TMA_L / TMA_T;
+    constexpr int HALF_ELEMS = TMA2_HALF_BYTES / 16;       // 2048
+    constexpr int TILE_ELEMS = TMA_TILE_BYTES / 16;        // 4096
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < 3; i++) { mbar_init(full_h + i, 1); mbar_init(freed_h + i, TMA_GROUP); }
+        for (int i = 0; i < 2; i++) { mbar_init(rd + i, TMA_GROUP); mbar_init(staged + i, TMA_GROUP); mbar_init(drained + i, 1); }
+        for (int i = 0; i < 4; i++) mbar_init(pd + i, TMA_GROUP);
+        *log_count = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int nitems = 2 * a.batch * TPT;
+    const int B = a.batch, D = a.delay, S = a.nslots;
+
+    if (warp >= 2 * TMA_GROUP / 32) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (tid == 2 * TMA_GROUP) {
+            // ------------------------------------------------------------ loader
+            int tokens = 0, ready_tf = -1;
+            long long hidx = 0;                             // halves issued so far
+            for (int it = 0; tokens < 2; it++) {
+                const int item = tokens ? nitems : atomicAdd(a.queue, 1);
+                const bool token = item >= nitems;
+                TmaItem w;
+                w.type = 0; w.tf = 0; w.c = 0;
+                const CUtensorMap* tm = &tm_x;
+                int tfc = 0;
+                if (!token) {
+                    w = tma_decode(item, B, D);
+                    if (w.type == 0) {
+                        if (w.tf >= S && !(a.dbg_nodeps & 2)) { while (ld_relaxed_gpu(a.done2 + (w.tf - S)) < TPT) __nanosleep(32); }
+                        tfc = w.tf;
+                    } else {
+                        if (w.tf != ready_tf) {             // one poll + fence pair per transform, not per tile
+                            if (!(a.dbg_nodeps & 1)) { while (ld_relaxed_gpu(a.done1 + w.tf) < TPT) __nanosleep(32); }
+                            asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+                            asm volatile("fence.proxy.async;\n" ::: "memory");  // other CTAs' generic-proxy stores -> this async-proxy read
+                            ready_tf = w.tf;
+                        }
+                        tm = &tm_int; tfc = w.tf % S;
+                    }
+                }
+                log[it & 31] = token ? -1 : item;
+                __threadfence_block();
+                *log_count = it + 1;
+                if (token) tokens++;
+#pragma unroll
+                for (int h = 0; h < 2; h++, hidx++) {
+                    const int s = (int)(hidx % TMA2_NSLOT);
+                    if (token) {                            // only the first half of a token is ever looked at (and never freed)
+                        if (h == 0) {
+                            if (hidx >= TMA2_NSLOT) mbar_wait(freed_h + s, (unsigned)(((hidx - TMA2_NSLOT) / TMA2_NSLOT) & 1));
+                            mbar_arrive(full_h + s);
+                        }
+                        continue;
+                    }
+                    if (hidx >= TMA2_NSLOT) mbar_wait(freed_h + s, (unsigned)(((hidx - TMA2_NSLOT) / TMA2_NSLOT) & 1));
+                    if (a.dbg_noload) { mbar_arrive(full_h + s); continue; }
+                    mbar_expect_tx(full_h + s, TMA2_HALF_BYTES);
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                        tma_load_3d(land + (size_t)s * HALF_ELEMS + j * TMA_BOX_ROWS * TMA_T, tm, w.c * 2 * TMA_T,
+                                    (2 * h + j) * TMA_BOX_ROWS, tfc, full_h + s);
+                }
+            }
+        } else if (tid == 2 * TMA_GROUP + 32) {
+            // ------------------------------------------------------------ storer of P2 tiles
+            unsigned np2[2] = {0, 0};
+            for (int it = 0;; it++) {
+                while (ld_volatile_shared(log_count) <= it) __nanosleep(64);
+                __threadfence_block();
+                const int item = log[it & 31];
+                if (item < 0) break;
+                const TmaItem pi = tma_decode(item, B, D);
+                if (pi.type != 1 || a.p2_stg) continue;
+                const int g = it & 1;
+                mbar_wait(staged + g, np2[g] & 1);
+                np2[g]++;
+                const cpx* srcb = work + (size_t)g * TILE_ELEMS;
+                if (!a.dbg_nop2st) {
+#pragma unroll
+                    for (int j = 0; j < TMA_L / TMA_BOX_ROWS; j++)
+                        tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T);
+                    tma_commit();
+                    tma_wait_read0();
+                }
+                mbar_arrive(drained + g);
+            }
+            tma_wait_all0();
+        } else if (tid == 2 * TMA_GROUP + 64) {
+            // ------------------------------------------------------------ publisher of P1 tiles
+            unsigned np1[2] = {0, 0};
+            for (int it = 0;; it++) {
+                while (ld_volatile_shared(log_count) <= it) __nanosleep(64);
+                __threadfence_block();
+                const int item = log[it & 31];
+                if (item < 0) break;
+                const TmaItem pi = tma_decode(item, B, D);
+                if (pi.type != 0) continue;
+                const int g = it & 1;
+                mbar_wait(pd + 2 * g + (np1[g] & 1), (np1[g] >> 1) & 1);
+                np1[g]++;
+                red_release_gpu(a.done1 + pi.tf, 1);       // cumulative: publishes the group's stores (ordered by the mbarrier)
+            }
+        }
+        return;
+    }
+
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    const int g = warp >> 2;
+    const int tig = tid & (TMA_GROUP - 1);
+    const int ell = tig & (TMA_T - 1), p = tig >> 2;
+    const int odd = p & 1;
+    cpx* wbuf = work + (size_t)g * TILE_ELEMS;
+    cpx w = __ldg(a.wl + p);
+    unsigned nrd = 0, np1 = 0, np2 = 0;                     // phases of rd[g] waited so far; P1 / P2 tiles of this group so far
+    bool prev_p2 = false, first = true;
+    for (int it = g;; it += 2) {
+        const long long h0 = 2LL * it;
+        const int s0 = (int)(h0 % TMA2_NSLOT), s1 = (int)((h0 + 1) % TMA2_NSLOT);
+        mbar_wait(full_h + s0, (unsigned)((h0 / TMA2_NSLOT) & 1));
+        const int item = log[it & 31];
+        if (item < 0) break;
+        const TmaItem wi = tma_decode(item, B, D);
+        const unsigned ld_conj = (a.ld_conj && wi.type == 0) ? 0x80000000u : 0u;
+        cpx x[32];
+        {
+            const cpx* s = land + (size_t)s0 * HALF_ELEMS + p * TMA_T + ell;
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = cconj_if(s[i * 32 * TMA_T], ld_conj);
+        }
+        mbar_arrive(freed_h + s0);
+        mbar_wait(full_h + s1, (unsigned)(((h0 + 1) / TMA2_NSLOT) & 1));
+        if (wi.type == 1 && tig == 0) red_relaxed_gpu(a.done2 + wi.tf, 1);      // this tile of Int has been read
+        {
+            const cpx* s = land + (size_t)s1 * HALF_ELEMS + p * TMA_T + ell;
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[16 + i] = cconj_if(s[i * 32 * TMA_T], ld_conj);
+        }
+        mbar_arrive(freed_h + s1);
+        dft32(x);
+        // the work buffer is free once the previous tile's gathers are done (P1) or its staged outputs have drained (P2)
+        if (!first) {
+            if (prev_p2) mbar_wait(drained + g, (np2 - 1) & 1);
+            else { mbar_wait(rd + g, nrd & 1); nrd++; }
+        }
+        first = false;
+        {
+            cpx* s = wbuf + p * TMA_T + ell;
+#pragma unroll
+            for (int r = 0; r < 32; r++) s[r * 32 * TMA_T] = x[r];
+        }
+        cpx t_lo0, t_hi0, t_lo1, t_hi1;
+        if (wi.type == 0) {
+            const unsigned long long mask = (1ULL << a.tw_log2m) - 1ULL;
+            const unsigned long long n2 = (unsigned long long)(wi.c * TMA_T + ell);
+            const unsigned long long e0 = (n2 * (unsigned long long)p) & mask, e1 = (n2 * 32ULL) & mask;
+            t_lo0 = __ldg(a.tw_lo + (e0 & 4095ULL)); t_hi0 = __ldg(a.tw_hi + (e0 >> 12));
+            t_lo1 = __ldg(a.tw_lo + (e1 & 4095ULL)); t_hi1 = __ldg(a.tw_hi + (e1 >> 12));
+        }
+        group_bar(1 + g);
+        {
+            const cpx* s = wbuf + (32 * p) * TMA_T + ell;
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[j] = s[(j ^ odd) * TMA_T];
+        }
+        mbar_arrive(rd + g);
+        if (odd) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) { cpx t = x[j]; x[j] = x[j + 1]; x[j + 1] = t; }
+        }
+        asm volatile("" : "+d"(w.x), "+d"(w.y));
+        mul_powers32(x, w);
+        dft32(x);
+        if (wi.type == 0) {
+            cpx* dst = a.scratch + (size_t)(wi.tf % S) * ((size_t)TMA_L * TMA_L) + (size_t)(wi.c * TMA_T + ell) * TMA_L + p;
+            const cpx t0 = cmul(t_hi0, t_lo0), s1c = cmul(t_hi1, t_lo1);
+            const cpx s2 = csqr(s1c), s4 = csqr(s2);
+            cpx t[4];
+            t[0] = t0; t[1] = cmul(t0, s1c); t[2] = cmul(t0, s2); t[3] = cmul(t[1], s2);
+            if (a.dbg_nop1st) {
+                cpx acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int bb = 0; bb < 8; bb++) {
+#pragma unroll
+                    for (int aa = 0; aa < 4; aa++) {
+                        acc = cadd(acc, cmul(x[4 * bb + aa], t[aa]));
+                        if (bb < 7) t[aa] = cmul(t[aa], s4);
+                    }
+                }
+                if (acc.x == 1.2345e-300) dst[0] = acc;
+            } else {
+#pragma unroll
+                for (int bb = 0; bb < 8; bb++) {
+#pragma unroll
+                    for (int aa = 0; aa < 4; aa++) {
+                        dst[32 * (4 * bb + aa)] = cmul(x[4 * bb + aa], t[aa]);
+                        if (bb < 7) t[aa] = cmul(t[aa], s4);
+                    }
+                }
+            }
+            mbar_arrive(pd + 2 * g + (np1 & 1));
+            np1++;
+            prev_p2 = false;
+        } else {
+            if (a.st_conj || a.scale != 1.0) {
+                const double sx = a.scale, sy = a.st_conj ? -a.scale : a.scale;
+#pragma unroll
+                for (int s = 0; s < 32; s++) x[s] = make_double2(x[s].x * sx, x[s].y * sy);
+            }
+            if (a.p2_stg) {
+                cpx* dst = a.out + (long long)wi.tf * a.out_dist + (long long)p * TMA_L + wi.c * TMA_T + ell;   // X[k1 + 1024 k2], k2 = p + 32 r
+#pragma unroll
+                for (int r = 0; r < 32; r++) __stcs(reinterpret_cast<double2*>(dst + (long long)r * 32 * TMA_L), x[r]);
+                prev_p2 = false;                             // nothing staged: the work buffer is free once the gathers are done
+            } else {
+                mbar_wait(rd + g, nrd & 1);                  // every gather of this tile is done: the slots may be overwritten
+                nrd++;
+                cpx* s = wbuf + p * TMA_T + ell;
+#pragma unroll
+                for (int r = 0; r < 32; r++) s[r * 32 * TMA_T] = x[r];
+                fence_proxy_async();
+                mbar_arrive(staged + g);
+                np2++;
+                prev_p2 = true;
+            }
+        }
+    }
 }
 
 }  // namespace gd

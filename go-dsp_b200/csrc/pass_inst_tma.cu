@@ -52,6 +52,7 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
     static bool attr_set = false;
     if (!attr_set) {
         GD_CUDA(cudaFuncSetAttribute(fft_tma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
+        GD_CUDA(cudaFuncSetAttribute(fft_tma_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
         attr_set = true;
     }
     TmaEncodeFn enc;
@@ -103,7 +104,8 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(counters)"); break; }
         const long long nitems = 2 * nb * (TMA_L / TMA_T);
         const int grid = (int)(nitems < d.num_sms ? nitems : d.num_sms);
-        fft_tma_fused_kernel<<<grid, TMA_THREADS, TMA_SMEM, st>>>(m_x, m_int, m_out, f);
+        if (d.tma_variant == 1) fft_tma_fused_kernel<<<grid, TMA_THREADS, TMA_SMEM, st>>>(m_x, m_int, m_out, f);
+        else fft_tma_fused2_kernel<<<grid, TMA_THREADS, TMA2_SMEM, st>>>(m_x, m_int, m_out, f);
         e = cudaGetLastError();
         if (e != cudaSuccess) { rc = cuda_fail(e, "fft_tma_fused_kernel launch"); break; }
         g_launches++;

@@ -143,18 +143,43 @@ def test_batched(gd, b, lg):
     assert rel_l2(out, x) <= TOL
 
 
-@pytest.mark.parametrize("opt", [("fused", 1), ("wide_tiles", 1), ("pass_scratch_mb", 16)])
-def test_alternative_schedules_agree(gd, opt):   # every planner variant must give the same transform
+SCHEDULE_DEFAULTS = {"tma": 2, "tma_delay": 1, "fused": 0, "wide_tiles": 0, "pass_scratch_mb": 1024, "w32": 2}
+
+
+@pytest.mark.parametrize("opts", [{"tma": 2}, {"tma": 1}, {"tma": 2, "tma_delay": 2}, {"tma": 2, "tma_delay": 0}, {"tma": 0},
+                                  {"tma": 0, "fused": 1}, {"tma": 0, "wide_tiles": 1}, {"tma": 0, "pass_scratch_mb": 16},
+                                  {"tma": 0, "w32": 0}, {"tma": 0, "w32": 5}])
+def test_alternative_schedules_agree(gd, opts):   # every planner variant of the 2^20-point transform must give the same result
     _, capi, L = gd
     x = oracle.splitmix_complex(6 << 20, 3).reshape(6, 1 << 20)
     want = oracle.fft_batch(x, threads=8)
-    out = np.empty_like(x)
-    capi.check(L.gd_set_option(opt[0].encode(), opt[1]))
+    out, back = np.empty_like(x), np.empty_like(x)
+    for k, v in opts.items():
+        capi.check(L.gd_set_option(k.encode(), v))
     try:
         capi.check(L.gd_fft_batch_c2c(x.ctypes.data, out.ctypes.data, 1 << 20, 6, 1))
+        capi.check(L.gd_fft_batch_c2c(out.ctypes.data, back.ctypes.data, 1 << 20, 6, -1))     # conj / scale hooks of the same schedule
     finally:
-        capi.check(L.gd_set_option(opt[0].encode(), {"fused": 0, "wide_tiles": 0, "pass_scratch_mb": 1024}[opt[0]]))
+        for k, v in SCHEDULE_DEFAULTS.items():
+            capi.check(L.gd_set_option(k.encode(), v))
     assert rel_l2(out, want) <= TOL
+    assert rel_l2(back, x) <= TOL
+
+
+def test_tma_fused_chunking(gd):                  # more than one 128-transform launch, a partial last chunk, in place
+    _, capi, L = gd
+    import torch
+    nb, n = 131, 1 << 20
+    x = torch.empty(nb * n * 2, dtype=torch.float64, device="cuda")
+    capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), nb * n * 2, 3, 0, None))
+    torch.cuda.synchronize()
+    rows = [0, 1, 127, 128, 130]
+    src = {r: x.view(nb, n * 2)[r].cpu().numpy().view(np.complex128).copy() for r in rows}
+    capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), x.data_ptr(), n, nb, 1, None))             # in == out
+    capi.check(L.gd_stream_sync(None))
+    for r in rows:
+        got = x.view(nb, n * 2)[r].cpu().numpy().view(np.complex128)
+        assert rel_l2(got, oracle.fft(src[r])) <= TOL, r
 
 
 # ----------------------------------------------------------------- FFT2 / FFTN

@@ -130,6 +130,7 @@ int main(int argc, char** argv) {
         CUtensorMap ms = make_map(enc, scratch, S, N, getenv("TMA_PROMO_INT") ? atoi(getenv("TMA_PROMO_INT")) : 0);
         mx = make_map(enc, x, nbuf, N, promo);
         CK(cudaFuncSetAttribute(fft_tma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
+        CK(cudaFuncSetAttribute(fft_tma_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
         cudaStream_t st; CK(cudaStreamCreate(&st));
         if (persist) {
             int maxp = 0, maxw = 0;
@@ -154,20 +155,23 @@ int main(int argc, char** argv) {
         f.hints = getenv("TMA_HINTS") ? atoi(getenv("TMA_HINTS")) : 0;
         f.p2_stg = getenv("TMA_P2STG") ? atoi(getenv("TMA_P2STG")) : 0;
         f.out = out; f.out_dist = N;
-        f.dbg_nodeps = getenv("TMA_NODEPS") ? 1 : 0;
+        f.dbg_nodeps = getenv("TMA_NODEPS") ? atoi(getenv("TMA_NODEPS")) : 0;
         f.dbg_nop1st = getenv("TMA_NOP1ST") ? 1 : 0;
+        f.dbg_nop2st = getenv("TMA_NOP2ST") ? 1 : 0;
+        f.dbg_noload = getenv("TMA_NOLOAD") ? 1 : 0;
         CK(cudaMemsetAsync(out, 0, nbuf * N * 16, st));
         float fb = 1e9;
         for (int i = 0; i < iters + 1; i++) {
             CK(cudaMemsetAsync(cnt, 0, (2 * batch + 1) * sizeof(int), st));
             cudaEventRecord(e0, st);
-            fft_tma_fused_kernel<<<grid, TMA_THREADS, TMA_SMEM, st>>>(mx, ms, mo, f);
+            if (fused == 2) fft_tma_fused2_kernel<<<grid, TMA_THREADS, TMA2_SMEM, st>>>(mx, ms, mo, f);
+            else fft_tma_fused_kernel<<<grid, TMA_THREADS, TMA_SMEM, st>>>(mx, ms, mo, f);
             cudaEventRecord(e1, st);
             CK(cudaStreamSynchronize(st));
             float m; cudaEventElapsedTime(&m, e0, e1);
             if (i > 0 && m < fb) fb = m;
         }
-        printf("FUSED batch %lld delay %d grid %d persist %d: %.3f ms = %.1f GS/s\n", batch, delay, grid, persist, fb, batch * N / fb / 1e6);
+        printf("FUSED%d batch %lld delay %d grid %d persist %d: %.3f ms = %.1f GS/s\n", fused, batch, delay, grid, persist, fb, batch * N / fb / 1e6);
         if (f.stats) {
             std::vector<long long> hs(grid * 12);
             CK(cudaMemcpy(hs.data(), dstats, grid * 12 * sizeof(long long), cudaMemcpyDeviceToHost));
