@@ -306,13 +306,13 @@ def run_ours(args):
                    "residency": "inputs and outputs resident in HBM (generated on device, SplitMix64 seed 3)",
                    "l2": "inputs (%.1f GiB per GPU) are far larger than L2; no flush needed" % (batch * n * 16 / 2**30),
                    "parallelism": "batch rows sharded over %d GPU(s), no collective" % world},
-        "roofline": {"bound": "hbm", "kernel": "gd::fft_pass_kernel<10,4,false> (both four-step passes are launches of this kernel)",
+        "roofline": {"bound": "hbm", "kernel": "gd::fft_tma_fused2_kernel (both four-step passes of up to 128 transforms per launch; the intermediate stays in L2)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "peak_source": peak_src, "traffic": ncu_traffic("fft_pass_kernel"),
-                     "traffic_note": "dram read+write bytes per launch from profiles/r1_ncu_full_summary.json (ncu --set full, 64-transform chunk): the two-launch four-step writes and re-reads the intermediate, so HBM traffic is 2x the algorithmic bytes",
+                     "peak_source": peak_src, "traffic": ncu_traffic("fft_tma_fused2_kernel"),
+                     "traffic_note": "dram read+write bytes per launch (128 transforms) from profiles/r1_ncu_full_summary.json (ncu --set full): equal to the algorithmic bytes, the inter-pass array never reaches HBM",
                      "algorithmic_bytes_per_launch": per_gpu_bytes / max(1.0, launches_per_step),
                      "avg_launch_us": ms * 1e3 / max(1.0, launches_per_step),
-                     "note": "32 B/point (16 read + 16 written once, SURVEY.md 8d) x points per step / CUDA-event step time; each launch is one pass over one chunk and is charged half"},
+                     "note": "32 B/point (16 read + 16 written once, SURVEY.md 8d) x points per launch / CUDA-event time per launch; FP64 issue (about 80 FP64 instructions per point) is the co-limiting roof, see DESIGN.md"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
 

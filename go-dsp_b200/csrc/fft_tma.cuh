@@ -254,7 +254,8 @@ struct TmaFusedParams {
     cpx* scratch;                // S slots of 2^20 elements
     int* done1;                  // [batch] zeroed by the host
     int* done2;                  // [batch]
-    int* queue;                  // next item of the sequence (zeroed by the host)
+    int* queue;                  // next item of the sequence; two_queues: queue[0] = next P1 tile, queue[1] = next P2 tile (zeroed by the host)
+    int two_queues;
     int dbg_nodeps;              // timing experiments only: ignore the global dependencies (results are garbage)
     int dbg_nop1st;              // timing experiments only: skip the pass-1 stores
     int dbg_nop2st, dbg_noload;  // timing experiments only: skip the pass-2 tile stores / the tile loads
@@ -625,6 +626,23 @@ constexpr int TMA2_SMEM = TMA2_NSLOT * TMA2_HALF_BYTES + 2 * TMA_TILE_BYTES + 10
 
 __device__ __forceinline__ int ld_volatile_shared(const volatile int* p) { return *p; }
 
+// Two-queue scheduling (a.two_queues): pass-1 tiles and pass-2 tiles are claimed from separate in-order queues.
+// A loader takes a P2 tile when the head transform of the P2 queue is fully published, otherwise a P1 tile when
+// its scratch slot is free, so the P1 stream runs as far ahead as the S slots allow (about two transforms with
+// S = 3) instead of the fixed one-phase distance of the single sequence -- the P1 -> P2 dependency then has slack
+// to spare without a fourth 16 MiB slot in L2. Item code: bit 30 = pass, low bits = tile index in that pass.
+// No deadlock: a P1 tile waits only for P2 tiles of an older transform whose P1 tiles are all claimed already,
+// and a P2 tile waits only for claimed P1 tiles; claimed tiles always finish.
+__device__ __forceinline__ TmaItem tma_decode2(int code) {
+    constexpr int TPT = TMA_L / TMA_T;
+    TmaItem it;
+    const int idx = code & 0x3FFFFFFF;
+    it.type = (code >> 30) & 1;
+    it.tf = idx / TPT;
+    it.c = idx % TPT;
+    return it;
+}
+
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_int,
                       const __grid_constant__ CUtensorMap tm_out, const TmaFusedParams a) {
@@ -636,10 +654,10 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     unsigned long long* freed_h = bars + 3;                // [3]
     unsigned long long* rd = bars + 6;                     // [2]
     unsigned long long* staged = bars + 8;                 // [2]
-    unsigned long long* drained = bars + 10;               // [2]
-    unsigned long long* pd = bars + 12;                    // [2][2]
-    volatile int* log = reinterpret_cast<volatile int*>(bars + 16);        // [32]
-    volatile int* log_count = reinterpret_cast<volatile int*>(bars + 32);  // local steps published by the loader
+    unsigned long long* drained = bars + 10;               // [2 groups][2 halves of the work buffer]
+    unsigned long long* pd = bars + 14;                    // [2][2]
+    volatile int* log = reinterpret_cast<volatile int*>(bars + 20);        // [32]
+    volatile int* log_count = reinterpret_cast<volatile int*>(bars + 36);  // local steps published by the loader
     constexpr int TPT = TMA_L / TMA_T;
     constexpr int HALF_ELEMS = TMA2_HALF_BYTES / 16;       // 2048
     constexpr int TILE_ELEMS = TMA_TILE_BYTES / 16;        // 4096
@@ -647,7 +665,8 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
         for (int i = 0; i < 3; i++) { mbar_init(full_h + i, 1); mbar_init(freed_h + i, TMA_GROUP); }
-        for (int i = 0; i < 2; i++) { mbar_init(rd + i, TMA_GROUP); mbar_init(staged + i, TMA_GROUP); mbar_init(drained + i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(rd + i, TMA_GROUP); mbar_init(staged + i, TMA_GROUP); }
+        for (int i = 0; i < 4; i++) mbar_init(drained + i, 1);
         for (int i = 0; i < 4; i++) mbar_init(pd + i, TMA_GROUP);
         *log_count = 0;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -662,13 +681,64 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             // ------------------------------------------------------------ loader
             int tokens = 0, ready_tf = -1;
             long long hidx = 0;                             // halves issued so far
+            int ready_tf2 = -1, free_tf1 = S - 1;       // transforms known to be published / whose slot is known to be free
+            const int ntiles = B * TPT;
             for (int it = 0; tokens < 2; it++) {
-                const int item = tokens ? nitems : atomicAdd(a.queue, 1);
-                const bool token = item >= nitems;
+                int item = nitems;
+                bool token = tokens != 0;
                 TmaItem w;
                 w.type = 0; w.tf = 0; w.c = 0;
                 const CUtensorMap* tm = &tm_x;
                 int tfc = 0;
+                if (a.two_queues) {
+                    // ---- two in-order queues; prefer the pass the previous step did not take
+                    int code = -1;
+                    bool fence_needed = false;
+                    while (!token && code < 0) {
+                        const int q2 = ld_relaxed_gpu(a.queue + 1), q1 = ld_relaxed_gpu(a.queue);
+                        if (q1 >= ntiles && q2 >= ntiles) { token = true; break; }
+                        bool ok2 = false, ok1 = false;
+                        if (q2 < ntiles) {
+                            const int gq = q2 / TPT;
+                            if (gq <= ready_tf2) ok2 = true;
+                            else if (ld_relaxed_gpu(a.done1 + gq) >= TPT) { ready_tf2 = gq; fence_needed = true; ok2 = true; }
+                        }
+                        if (q1 < ntiles) {
+                            const int hq = q1 / TPT;
+                            if (hq <= free_tf1) ok1 = true;
+                            else if (ld_relaxed_gpu(a.done2 + (hq - S)) >= TPT) { free_tf1 = hq; ok1 = true; }
+                        }
+                        const bool prefer2 = a.two_queues == 1 ? (it & 1) == 0 : a.two_queues == 2 ? true : a.two_queues == 3 ? false : ((it >> 1) & 1) == 0;
+                        int pick = -1;
+                        if (ok2 && (prefer2 || !ok1)) pick = 1; else if (ok1) pick = 0;
+                        if (pick < 0) { __nanosleep(64); continue; }
+                        const int idx = atomicAdd(a.queue + pick, 1);
+                        if (idx >= ntiles) continue;            // lost the race for the last tile of that pass
+                        code = (pick << 30) | idx;
+                        const int tfq = idx / TPT;
+                        if (pick == 1 && tfq > ready_tf2) {    // the head moved on to the next transform meanwhile: wait for it
+                            while (ld_relaxed_gpu(a.done1 + tfq) < TPT) __nanosleep(32);
+                            ready_tf2 = tfq; fence_needed = true;
+                        }
+                        if (pick == 0 && tfq > free_tf1) {
+                            while (ld_relaxed_gpu(a.done2 + (tfq - S)) < TPT) __nanosleep(32);
+                            free_tf1 = tfq;
+                        }
+                    }
+                    if (!token) {
+                        w = tma_decode2(code);
+                        item = code;
+                        if (w.type == 1) {
+                            if (fence_needed) {
+                                asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+                                asm volatile("fence.proxy.async;\n" ::: "memory");
+                            }
+                            tm = &tm_int; tfc = w.tf % S;
+                        } else tfc = w.tf;
+                    }
+                } else {
+                item = tokens ? nitems : atomicAdd(a.queue, 1);
+                token = item >= nitems;
                 if (!token) {
                     w = tma_decode(item, B, D);
                     if (w.type == 0) {
@@ -683,6 +753,7 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                         }
                         tm = &tm_int; tfc = w.tf % S;
                     }
+                }
                 }
                 log[it & 31] = token ? -1 : item;
                 __threadfence_block();
@@ -715,20 +786,28 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 __threadfence_block();
                 const int item = log[it & 31];
                 if (item < 0) break;
-                const TmaItem pi = tma_decode(item, B, D);
+                const TmaItem pi = a.two_queues ? tma_decode2(item) : tma_decode(item, B, D);
                 if (pi.type != 1 || a.p2_stg) continue;
                 const int g = it & 1;
                 mbar_wait(staged + g, np2[g] & 1);
                 np2[g]++;
                 const cpx* srcb = work + (size_t)g * TILE_ELEMS;
+                // two bulk groups, rows 0..511 and 512..1023: the group's next exchange may refill the first half of the
+                // work buffer while the second is still being read out
                 if (!a.dbg_nop2st) {
 #pragma unroll
-                    for (int j = 0; j < TMA_L / TMA_BOX_ROWS; j++)
+                    for (int j = 0; j < 2; j++)
                         tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T);
                     tma_commit();
-                    tma_wait_read0();
+#pragma unroll
+                    for (int j = 2; j < 4; j++)
+                        tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T);
+                    tma_commit();
+                    asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
                 }
-                mbar_arrive(drained + g);
+                mbar_arrive(drained + 2 * g);
+                if (!a.dbg_nop2st) tma_wait_read0();
+                mbar_arrive(drained + 2 * g + 1);
             }
             tma_wait_all0();
         } else if (tid == 2 * TMA_GROUP + 64) {
@@ -739,7 +818,7 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 __threadfence_block();
                 const int item = log[it & 31];
                 if (item < 0) break;
-                const TmaItem pi = tma_decode(item, B, D);
+                const TmaItem pi = a.two_queues ? tma_decode2(item) : tma_decode(item, B, D);
                 if (pi.type != 0) continue;
                 const int g = it & 1;
                 mbar_wait(pd + 2 * g + (np1[g] & 1), (np1[g] >> 1) & 1);
@@ -765,7 +844,7 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         mbar_wait(full_h + s0, (unsigned)((h0 / TMA2_NSLOT) & 1));
         const int item = log[it & 31];
         if (item < 0) break;
-        const TmaItem wi = tma_decode(item, B, D);
+        const TmaItem wi = a.two_queues ? tma_decode2(item) : tma_decode(item, B, D);
         const unsigned ld_conj = (a.ld_conj && wi.type == 0) ? 0x80000000u : 0u;
         cpx x[32];
         {
@@ -785,15 +864,18 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         dft32(x);
         // the work buffer is free once the previous tile's gathers are done (P1) or its staged outputs have drained (P2)
         if (!first) {
-            if (prev_p2) mbar_wait(drained + g, (np2 - 1) & 1);
+            if (prev_p2) mbar_wait(drained + 2 * g, (np2 - 1) & 1);
             else { mbar_wait(rd + g, nrd & 1); nrd++; }
         }
-        first = false;
         {
             cpx* s = wbuf + p * TMA_T + ell;
 #pragma unroll
-            for (int r = 0; r < 32; r++) s[r * 32 * TMA_T] = x[r];
+            for (int r = 0; r < 16; r++) s[r * 32 * TMA_T] = x[r];                          // rows p + 32 r < 512
+            if (!first && prev_p2) mbar_wait(drained + 2 * g + 1, (np2 - 1) & 1);
+#pragma unroll
+            for (int r = 16; r < 32; r++) s[r * 32 * TMA_T] = x[r];
         }
+        first = false;
         cpx t_lo0, t_hi0, t_lo1, t_hi1;
         if (wi.type == 0) {
             const unsigned long long mask = (1ULL << a.tw_log2m) - 1ULL;

@@ -66,7 +66,7 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
     GD_TRY(d.ensure_scratch(SCR_TMA, scr_bytes, (void**)&scratch));
     const long long CH = 128;               // transforms per launch: one tensor map per array, item ids stay small
     int* cnt;
-    GD_TRY(d.ensure_scratch(SCR_CNT, (2 * (size_t)CH + 1) * sizeof(int), (void**)&cnt));
+    GD_TRY(d.ensure_scratch(SCR_CNT, (2 * (size_t)CH + 2) * sizeof(int), (void**)&cnt));
     CUtensorMap m_int;
     GD_TRY(tma_map(enc, scratch, S, N, &m_int));
     // keep the scratch slots resident in L2: persisting access-policy window while the launches run
@@ -100,7 +100,8 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.wl = d.wl[10]; f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.tw_log2m = 20;
         f.ld_conj = ld_conj; f.st_conj = st_conj; f.scale = scale;
-        cudaError_t e = cudaMemsetAsync(cnt, 0, (2 * (size_t)CH + 1) * sizeof(int), st);
+        f.two_queues = d.tma_variant == 2 ? d.tma_two_queues : 0;
+        cudaError_t e = cudaMemsetAsync(cnt, 0, (2 * (size_t)CH + 2) * sizeof(int), st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(counters)"); break; }
         const long long nitems = 2 * nb * (TMA_L / TMA_T);
         const int grid = (int)(nitems < d.num_sms ? nitems : d.num_sms);

@@ -125,7 +125,7 @@ int main(int argc, char** argv) {
         const int S = delay + 2;
         cpx* scratch; int* cnt;
         CK(cudaMalloc(&scratch, (size_t)S * N * 16));
-        CK(cudaMalloc(&cnt, (2 * batch + 1) * sizeof(int)));
+        CK(cudaMalloc(&cnt, (2 * batch + 2) * sizeof(int)));
         const int promo = getenv("TMA_PROMO") ? atoi(getenv("TMA_PROMO")) : 0;
         CUtensorMap ms = make_map(enc, scratch, S, N, getenv("TMA_PROMO_INT") ? atoi(getenv("TMA_PROMO_INT")) : 0);
         mx = make_map(enc, x, nbuf, N, promo);
@@ -158,11 +158,12 @@ int main(int argc, char** argv) {
         f.dbg_nodeps = getenv("TMA_NODEPS") ? atoi(getenv("TMA_NODEPS")) : 0;
         f.dbg_nop1st = getenv("TMA_NOP1ST") ? 1 : 0;
         f.dbg_nop2st = getenv("TMA_NOP2ST") ? 1 : 0;
+        f.two_queues = getenv("TMA_2Q") ? atoi(getenv("TMA_2Q")) : 0;
         f.dbg_noload = getenv("TMA_NOLOAD") ? 1 : 0;
         CK(cudaMemsetAsync(out, 0, nbuf * N * 16, st));
         float fb = 1e9;
         for (int i = 0; i < iters + 1; i++) {
-            CK(cudaMemsetAsync(cnt, 0, (2 * batch + 1) * sizeof(int), st));
+            CK(cudaMemsetAsync(cnt, 0, (2 * batch + 2) * sizeof(int), st));
             cudaEventRecord(e0, st);
             if (fused == 2) fft_tma_fused2_kernel<<<grid, TMA_THREADS, TMA2_SMEM, st>>>(mx, ms, mo, f);
             else fft_tma_fused_kernel<<<grid, TMA_THREADS, TMA_SMEM, st>>>(mx, ms, mo, f);
