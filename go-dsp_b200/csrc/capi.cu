@@ -147,8 +147,9 @@ int gd_set_option(const char* key, int64_t value) {
     else if (!strcmp(key, "fused")) d.use_fused = value != 0;
     else if (!strcmp(key, "debug_alias")) d.debug_alias = value != 0;
     else if (!strcmp(key, "w32")) { if (value < 0 || value > 6) return (int)invalid_arg("w32 out of range"); d.w32 = (int)value; }
-    else if (!strcmp(key, "tma")) { if (value < 0 || value > 2) return (int)invalid_arg("tma out of range"); d.use_tma = value != 0; if (value) d.tma_variant = (int)value; }
+    else if (!strcmp(key, "tma")) d.use_tma = value != 0;
     else if (!strcmp(key, "tma_two_queues")) { if (value < 0 || value > 4) return (int)invalid_arg("tma_two_queues out of range"); d.tma_two_queues = (int)value; }
+    else if (!strcmp(key, "tma_dbg")) d.tma_dbg = (int)value;
     else if (!strcmp(key, "tma_delay")) { if (value < 0 || value > 4) return (int)invalid_arg("tma_delay out of range"); d.tma_delay = (int)value; }
     else if (!strcmp(key, "tiled_scratch")) d.tiled_scratch = value != 0;
     else if (!strcmp(key, "l2_window")) d.use_l2_window = value != 0;

@@ -90,8 +90,8 @@ struct Device {
     bool use_fused = false;              // one persistent kernel for both four-step passes (N = L*L), L2-resident scratch
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)
-    int tma_variant = 2;                 // 2 = landing slots decoupled from the work buffers (fft_tma_fused2_kernel), 1 = three tile buffers
     int tma_two_queues = 0;              // separate in-order queues for pass-1 / pass-2 tiles (measured slower: the P1/P2 mix per SM drifts)
+    int tma_dbg = 0;                     // bisecting switches of the fused kernel (bit 0: acquire load instead of fence, bit 1: unsplit drain, bit 2: no fence by the storing warps, bit 3: writer-side proxy fence)
     int tma_delay = 1;                   // phases between P1(g) and P2(g); delay + 2 slots of 16 MiB must stay in L2
     std::recursive_mutex mu;             // every public entry point locks its device
 

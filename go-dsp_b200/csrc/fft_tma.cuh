@@ -77,6 +77,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {      // non-blocking
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned long long* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
@@ -91,6 +101,10 @@ __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "n"(TMA_GROUP) : "memory"); }
 
+// NOTE: fft_tma_kernel (one pass per launch) and fft_tma_fused_kernel (first fused version) are measurement kernels for
+// tools/ubench/tma_pass.cu and are not reachable from the C ABI. The product is fft_tma_fused2_kernel below; in
+// particular the first fused version hands P1 tiles to its publisher without a device-scope fence by the storing
+// warps and lets helper lanes follow mbarrier phases they do not own, both of which the stress test showed to be unsafe.
 template <int OUTMODE>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fft_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const TmaPassParams a) {
@@ -98,13 +112,14 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     // buffers first (TMA destinations: 128-byte aligned), barriers after them
     cpx* bufs = reinterpret_cast<cpx*>(smem_raw);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + TMA_NBUF * TMA_TILE_BYTES);
-    unsigned long long* full = bars;              // [NBUF] tile landed (tx bytes)
-    unsigned long long* freed = bars + TMA_NBUF;  // [NBUF] OUT_ROWS: inputs consumed; OUT_TILE: outputs staged   (128 arrivals)
-    unsigned long long* rd = bars + 2 * TMA_NBUF; // [2] per group: every gather of the tile is done             (128 arrivals)
+    // full is per (buffer, consumer group): a parity wait is only safe when the waiter observes every phase of its barrier
+    unsigned long long* full = bars;              // [NBUF][2] tile landed (tx bytes)
+    unsigned long long* freed = bars + 2 * TMA_NBUF;  // [NBUF] OUT_ROWS: inputs consumed; OUT_TILE: outputs staged   (128 arrivals)
+    unsigned long long* rd = bars + 3 * TMA_NBUF; // [2] per group: every gather of the tile is done             (128 arrivals)
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < TMA_NBUF; i++) { mbar_init(full + i, 1); mbar_init(freed + i, TMA_GROUP); }
+        for (int i = 0; i < TMA_NBUF; i++) { mbar_init(full + 2 * i, 1); mbar_init(full + 2 * i + 1, 1); mbar_init(freed + i, TMA_GROUP); }
         mbar_init(rd + 0, TMA_GROUP); mbar_init(rd + 1, TMA_GROUP);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -134,11 +149,12 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                 }
                 const long long tile = blockIdx.x + it * gridDim.x;
                 const int tf = (int)(tile / TPT) & a.tf_mask, c = (int)(tile % TPT);
-                if (a.dbg_noload) { mbar_arrive(full + b); continue; }
-                mbar_expect_tx(full + b, TMA_TILE_BYTES);
+                unsigned long long* fb = full + 2 * b + (int)(it & 1);
+                if (a.dbg_noload) { mbar_arrive(fb); continue; }
+                mbar_expect_tx(fb, TMA_TILE_BYTES);
 #pragma unroll
                 for (int j = 0; j < TMA_L / TMA_BOX_ROWS; j++)
-                    tma_load_3d(bufs + (size_t)b * (TMA_TILE_BYTES / 16) + j * TMA_BOX_ROWS * TMA_T, &tm_in, c * 2 * TMA_T, j * TMA_BOX_ROWS, tf, full + b);
+                    tma_load_3d(bufs + (size_t)b * (TMA_TILE_BYTES / 16) + j * TMA_BOX_ROWS * TMA_T, &tm_in, c * 2 * TMA_T, j * TMA_BOX_ROWS, tf, fb);
             }
             if (OUTMODE == TMA_OUT_TILE && !a.dbg_nostore) {
                 for (long long it = my_tiles > TMA_NBUF ? my_tiles - TMA_NBUF : 0; it < my_tiles; it++) {
@@ -171,7 +187,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         cpx* base = bufs + (size_t)b * (TMA_TILE_BYTES / 16);
         const long long tile = blockIdx.x + it * gridDim.x;
         const int tf = (int)(tile / TPT) & a.tf_mask, c = (int)(tile % TPT);
-        mbar_wait(full + b, (unsigned)((it / TMA_NBUF) & 1));
+        mbar_wait(full + 2 * b + g, (unsigned)((it / (2 * TMA_NBUF)) & 1));   // (buffer, group) recurs every 6 steps
         cpx x[32];
         {
             const cpx* s = base + p * TMA_T + ell;
@@ -256,6 +272,11 @@ struct TmaFusedParams {
     int* done2;                  // [batch]
     int* queue;                  // next item of the sequence; two_queues: queue[0] = next P1 tile, queue[1] = next P2 tile (zeroed by the host)
     int two_queues;
+    int dbg_acqload;             // measurement only: acquire with a load instead of fence.acq_rel.gpu
+    int dbg_nosplit;             // measurement only: free the whole work buffer at once after a P2 store
+    int dbg_wproxy;              // measurement only: writer-side generic->async proxy fence after the P1 stores
+    int dbg_nopubfence;          // measurement only: drop the storing warps' device-scope fence (then results are occasionally wrong)
+    int dbg_out_alias, dbg_in_alias;   // measurement only: mask of transform-index bits cleared for the output / input (keeps them in L2)
     int dbg_nodeps;              // timing experiments only: ignore the global dependencies (results are garbage)
     int dbg_nop1st;              // timing experiments only: skip the pass-1 stores
     int dbg_nop2st, dbg_noload;  // timing experiments only: skip the pass-2 tile stores / the tile loads
@@ -347,18 +368,18 @@ fft_tma_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     cpx* bufs = reinterpret_cast<cpx*>(smem_raw);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + TMA_NBUF * TMA_TILE_BYTES);
-    unsigned long long* full = bars;
-    unsigned long long* freed = bars + TMA_NBUF;
-    unsigned long long* empty = bars + 2 * TMA_NBUF;
-    unsigned long long* rd = bars + 3 * TMA_NBUF;
-    unsigned long long* pd = bars + 3 * TMA_NBUF + 2;      // [2 groups][2]
-    volatile int* log = reinterpret_cast<volatile int*>(bars + 16);   // [32] item ids by local step
-    volatile long long* tissue = reinterpret_cast<volatile long long*>(bars + 32);   // [32] load issue times (stats only)
+    unsigned long long* full = bars;                       // [NBUF][2 groups]: see fft_tma_fused2_kernel for why per group
+    unsigned long long* freed = bars + 2 * TMA_NBUF;
+    unsigned long long* empty = bars + 3 * TMA_NBUF;
+    unsigned long long* rd = bars + 4 * TMA_NBUF;
+    unsigned long long* pd = bars + 4 * TMA_NBUF + 2;      // [2 groups][2]
+    volatile int* log = reinterpret_cast<volatile int*>(bars + 20);   // [32] item ids by local step
+    volatile long long* tissue = reinterpret_cast<volatile long long*>(bars + 36);   // [32] load issue times (stats only)
     constexpr int TPT = TMA_L / TMA_T;
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < TMA_NBUF; i++) { mbar_init(full + i, 1); mbar_init(freed + i, TMA_GROUP); mbar_init(empty + i, 1); }
+        for (int i = 0; i < TMA_NBUF; i++) { mbar_init(full + 2 * i, 1); mbar_init(full + 2 * i + 1, 1); mbar_init(freed + i, TMA_GROUP); mbar_init(empty + i, 1); }
         mbar_init(rd + 0, TMA_GROUP); mbar_init(rd + 1, TMA_GROUP);
         for (int i = 0; i < 4; i++) mbar_init(pd + i, TMA_GROUP);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -418,24 +439,25 @@ fft_tma_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 if (token) {                                // no more work: one token per consumer group
                     log[it & 31] = -1;
                     prev_p2 &= ~(1u << b);
-                    mbar_arrive(full + b);
+                    mbar_arrive(full + 2 * b + (int)(it & 1));
                     tokens++;
                     continue;
                 }
                 if (w.type == 0) prev_p2 &= ~(1u << b); else prev_p2 |= 1u << b;
                 log[it & 31] = item;
                 if (a.stats) tissue[it & 31] = clock64();
-                mbar_expect_tx(full + b, TMA_TILE_BYTES);   // release: the log entry is visible to whoever sees the phase
+                unsigned long long* fb = full + 2 * b + (int)(it & 1);
+                mbar_expect_tx(fb, TMA_TILE_BYTES);         // release: the log entry is visible to whoever sees the phase
                 cpx* dstb = bufs + (size_t)b * (TMA_TILE_BYTES / 16);
                 if (a.hints) {
                     const unsigned long long pol = w.type == 0 ? pol_first : pol_last;
 #pragma unroll
                     for (int j = 0; j < TMA_L / TMA_BOX_ROWS; j++)
-                        tma_load_3d_hint(dstb + j * TMA_BOX_ROWS * TMA_T, tm, w.c * 2 * TMA_T, j * TMA_BOX_ROWS, tfc, full + b, pol);
+                        tma_load_3d_hint(dstb + j * TMA_BOX_ROWS * TMA_T, tm, w.c * 2 * TMA_T, j * TMA_BOX_ROWS, tfc, fb, pol);
                 } else {
 #pragma unroll
                     for (int j = 0; j < TMA_L / TMA_BOX_ROWS; j++)
-                        tma_load_3d(dstb + j * TMA_BOX_ROWS * TMA_T, tm, w.c * 2 * TMA_T, j * TMA_BOX_ROWS, tfc, full + b);
+                        tma_load_3d(dstb + j * TMA_BOX_ROWS * TMA_T, tm, w.c * 2 * TMA_T, j * TMA_BOX_ROWS, tfc, fb);
                 }
             }
             if (a.stats) {
@@ -491,7 +513,7 @@ fft_tma_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             long long lat1 = 0, lat2 = 0, n1 = 0, n2 = 0;
             for (long long it = 0;; it++) {
                 const int b = (int)(it % TMA_NBUF);
-                mbar_wait(full + b, (unsigned)((it / TMA_NBUF) & 1));
+                mbar_wait(full + 2 * b + (int)(it & 1), (unsigned)((it / (2 * TMA_NBUF)) & 1));
                 const long long t = clock64();
                 const int item = log[it & 31];
                 if (item < 0) break;
@@ -517,9 +539,9 @@ fft_tma_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         cpx* base = bufs + (size_t)b * (TMA_TILE_BYTES / 16);
         if (a.stats) {
             const long long t0 = clock64();
-            mbar_wait(full + b, (unsigned)((it / TMA_NBUF) & 1));
+            mbar_wait(full + 2 * b + g, (unsigned)((it / (2 * TMA_NBUF)) & 1));
             c_full += clock64() - t0;
-        } else mbar_wait(full + b, (unsigned)((it / TMA_NBUF) & 1));
+        } else mbar_wait(full + 2 * b + g, (unsigned)((it / (2 * TMA_NBUF)) & 1));
         const int item = log[it & 31];
         if (item < 0) { mbar_arrive(freed + b); break; }   // lets the storer and the publisher see the token too
         const TmaItem wi = tma_decode(item, B, D);
@@ -650,21 +672,26 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     cpx* land = reinterpret_cast<cpx*>(smem_raw);
     cpx* work = reinterpret_cast<cpx*>(smem_raw + TMA2_NSLOT * TMA2_HALF_BYTES);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + TMA2_NSLOT * TMA2_HALF_BYTES + 2 * TMA_TILE_BYTES);
-    unsigned long long* full_h = bars;                     // [3]
-    unsigned long long* freed_h = bars + 3;                // [3]
-    unsigned long long* rd = bars + 6;                     // [2]
-    unsigned long long* staged = bars + 8;                 // [2]
-    unsigned long long* drained = bars + 10;               // [2 groups][2 halves of the work buffer]
-    unsigned long long* pd = bars + 14;                    // [2][2]
-    volatile int* log = reinterpret_cast<volatile int*>(bars + 20);        // [32]
-    volatile int* log_count = reinterpret_cast<volatile int*>(bars + 36);  // local steps published by the loader
+    // full_h is per (slot, consumer group): a parity wait is only safe for a waiter that observes EVERY phase of its
+    // barrier in order. With one barrier per slot, group B could reach its wait for phase k+1 while phase k -- a half
+    // of group A's tile, issued earlier but landing later (HBM vs L2) -- was still open; the parity test then
+    // succeeds at once and B reads a slot that has not landed.
+    unsigned long long* full_h = bars;                     // [3 slots][2 groups]
+    unsigned long long* freed_h = bars + 6;                // [3]
+    unsigned long long* rd = bars + 9;                     // [2]
+    unsigned long long* staged = bars + 11;                // [2]
+    unsigned long long* drained = bars + 13;               // [2 groups][2 halves of the work buffer]
+    unsigned long long* pd = bars + 17;                    // [2][2]
+    volatile int* log = reinterpret_cast<volatile int*>(bars + 22);        // [32]
+    volatile int* log_count = reinterpret_cast<volatile int*>(bars + 38);  // local steps published by the loader
     constexpr int TPT = TMA_L / TMA_T;
     constexpr int HALF_ELEMS = TMA2_HALF_BYTES / 16;       // 2048
     constexpr int TILE_ELEMS = TMA_TILE_BYTES / 16;        // 4096
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < 3; i++) { mbar_init(full_h + i, 1); mbar_init(freed_h + i, TMA_GROUP); }
+        for (int i = 0; i < 6; i++) mbar_init(full_h + i, 1);
+        for (int i = 0; i < 3; i++) mbar_init(freed_h + i, TMA_GROUP);
         for (int i = 0; i < 2; i++) { mbar_init(rd + i, TMA_GROUP); mbar_init(staged + i, TMA_GROUP); }
         for (int i = 0; i < 4; i++) mbar_init(drained + i, 1);
         for (int i = 0; i < 4; i++) mbar_init(pd + i, TMA_GROUP);
@@ -747,8 +774,17 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     } else {
                         if (w.tf != ready_tf) {             // one poll + fence pair per transform, not per tile
                             if (!(a.dbg_nodeps & 1)) { while (ld_relaxed_gpu(a.done1 + w.tf) < TPT) __nanosleep(32); }
-                            asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
-                            asm volatile("fence.proxy.async;\n" ::: "memory");  // other CTAs' generic-proxy stores -> this async-proxy read
+                            // Acquire with a full fence. An acquire load + fence.proxy.async.global is about 2.5 % faster (the
+                            // MEMBAR also waits for this lane's own tile loads in flight, ~2000 cycles on the phase boundary), but
+                            // the stress test still showed a stale tile about once per 1500 runs of 256 transforms at delay 2 with
+                            // it (0 of 2000 with the fences), so the fences stay; `dbg_acqload` keeps the variant measurable.
+                            if (a.dbg_acqload) {
+                                (void)ld_acquire_gpu(a.done1 + w.tf);
+                                asm volatile("fence.proxy.async.global;\n" ::: "memory");
+                            } else {
+                                asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+                                asm volatile("fence.proxy.async;\n" ::: "memory");   // other CTAs' generic-proxy stores -> this async-proxy read
+                            }
                             ready_tf = w.tf;
                         }
                         tm = &tm_int; tfc = w.tf % S;
@@ -765,17 +801,18 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     if (token) {                            // only the first half of a token is ever looked at (and never freed)
                         if (h == 0) {
                             if (hidx >= TMA2_NSLOT) mbar_wait(freed_h + s, (unsigned)(((hidx - TMA2_NSLOT) / TMA2_NSLOT) & 1));
-                            mbar_arrive(full_h + s);
+                            mbar_arrive(full_h + 2 * s + (it & 1));
                         }
                         continue;
                     }
                     if (hidx >= TMA2_NSLOT) mbar_wait(freed_h + s, (unsigned)(((hidx - TMA2_NSLOT) / TMA2_NSLOT) & 1));
-                    if (a.dbg_noload) { mbar_arrive(full_h + s); continue; }
-                    mbar_expect_tx(full_h + s, TMA2_HALF_BYTES);
+                    unsigned long long* fb = full_h + 2 * s + (it & 1);
+                    if (a.dbg_noload) { mbar_arrive(fb); continue; }
+                    mbar_expect_tx(fb, TMA2_HALF_BYTES);
 #pragma unroll
                     for (int j = 0; j < 2; j++)
                         tma_load_3d(land + (size_t)s * HALF_ELEMS + j * TMA_BOX_ROWS * TMA_T, tm, w.c * 2 * TMA_T,
-                                    (2 * h + j) * TMA_BOX_ROWS, tfc, full_h + s);
+                                    (2 * h + j) * TMA_BOX_ROWS, (w.type == 0 ? tfc & ~a.dbg_in_alias : tfc), fb);
                 }
             }
         } else if (tid == 2 * TMA_GROUP + 32) {
@@ -797,13 +834,14 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (!a.dbg_nop2st) {
 #pragma unroll
                     for (int j = 0; j < 2; j++)
-                        tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T);
+                        tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf & ~a.dbg_out_alias, srcb + j * TMA_BOX_ROWS * TMA_T);
                     tma_commit();
 #pragma unroll
                     for (int j = 2; j < 4; j++)
-                        tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T);
+                        tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf & ~a.dbg_out_alias, srcb + j * TMA_BOX_ROWS * TMA_T);
                     tma_commit();
-                    asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+                    if (a.dbg_nosplit) tma_wait_read0();
+                    else asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
                 }
                 mbar_arrive(drained + 2 * g);
                 if (!a.dbg_nop2st) tma_wait_read0();
@@ -838,10 +876,12 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     cpx w = __ldg(a.wl + p);
     unsigned nrd = 0, np1 = 0, np2 = 0;                     // phases of rd[g] waited so far; P1 / P2 tiles of this group so far
     bool prev_p2 = false, first = true;
+    unsigned fph = 0;                                       // phase bit of full_h[slot][g], one per slot
     for (int it = g;; it += 2) {
         const long long h0 = 2LL * it;
         const int s0 = (int)(h0 % TMA2_NSLOT), s1 = (int)((h0 + 1) % TMA2_NSLOT);
-        mbar_wait(full_h + s0, (unsigned)((h0 / TMA2_NSLOT) & 1));
+        mbar_wait(full_h + 2 * s0 + g, (fph >> s0) & 1);
+        fph ^= 1u << s0;
         const int item = log[it & 31];
         if (item < 0) break;
         const TmaItem wi = a.two_queues ? tma_decode2(item) : tma_decode(item, B, D);
@@ -853,7 +893,8 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             for (int i = 0; i < 16; i++) x[i] = cconj_if(s[i * 32 * TMA_T], ld_conj);
         }
         mbar_arrive(freed_h + s0);
-        mbar_wait(full_h + s1, (unsigned)(((h0 + 1) / TMA2_NSLOT) & 1));
+        mbar_wait(full_h + 2 * s1 + g, (fph >> s1) & 1);
+        fph ^= 1u << s1;
         if (wi.type == 1 && tig == 0) red_relaxed_gpu(a.done2 + wi.tf, 1);      // this tile of Int has been read
         {
             const cpx* s = land + (size_t)s1 * HALF_ELEMS + p * TMA_T + ell;
@@ -925,6 +966,13 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     }
                 }
             }
+            // device-scope fence by every storing warp before the hand-off. Measured with tools/stress_fft.py (400 x 256
+            // transforms each): a release issued only by the publisher lane (another warp, mbarrier hand-off) gave wrong
+            // rows in 15 of 400 runs at delay 2 and 1 of 150 at delay 1 -- P2 tiles loaded rows of Int that had not reached
+            // L2 -- and so did "bar.sync, then one thread fences and releases" (17 of 400); with this fence 0 of 1100.
+            // It costs about 6 % (the warp waits for its stores to be acknowledged before it can start the next tile).
+            if (!a.dbg_nopubfence) asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+            if (a.dbg_wproxy) asm volatile("fence.proxy.async.global;\n" ::: "memory");
             mbar_arrive(pd + 2 * g + (np1 & 1));
             np1++;
             prev_p2 = false;

@@ -51,7 +51,6 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
                     int st_conj, double scale, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        GD_CUDA(cudaFuncSetAttribute(fft_tma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
         GD_CUDA(cudaFuncSetAttribute(fft_tma_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
         attr_set = true;
     }
@@ -100,13 +99,13 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.wl = d.wl[10]; f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.tw_log2m = 20;
         f.ld_conj = ld_conj; f.st_conj = st_conj; f.scale = scale;
-        f.two_queues = d.tma_variant == 2 ? d.tma_two_queues : 0;
+        f.two_queues = d.tma_two_queues;
+        f.dbg_acqload = d.tma_dbg & 1; f.dbg_nosplit = (d.tma_dbg >> 1) & 1; f.dbg_nopubfence = (d.tma_dbg >> 2) & 1; f.dbg_wproxy = (d.tma_dbg >> 3) & 1;
         cudaError_t e = cudaMemsetAsync(cnt, 0, (2 * (size_t)CH + 2) * sizeof(int), st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(counters)"); break; }
         const long long nitems = 2 * nb * (TMA_L / TMA_T);
         const int grid = (int)(nitems < d.num_sms ? nitems : d.num_sms);
-        if (d.tma_variant == 1) fft_tma_fused_kernel<<<grid, TMA_THREADS, TMA_SMEM, st>>>(m_x, m_int, m_out, f);
-        else fft_tma_fused2_kernel<<<grid, TMA_THREADS, TMA2_SMEM, st>>>(m_x, m_int, m_out, f);
+        fft_tma_fused2_kernel<<<grid, TMA_THREADS, TMA2_SMEM, st>>>(m_x, m_int, m_out, f);
         e = cudaGetLastError();
         if (e != cudaSuccess) { rc = cuda_fail(e, "fft_tma_fused_kernel launch"); break; }
         g_launches++;

@@ -74,6 +74,37 @@ func Convolve(x, y []complex128) []complex128 {
 	return r
 }
 
+// FFTBatch is additive (go-dsp has no batch call, SURVEY.md 8f rank 1): x holds len(x)/n transforms of n points
+// back to back; the result has the same layout. One cgo call, chunked H2D / kernels / D2H overlap inside the library;
+// slices wrapped around gd_pinned_alloc memory (PinnedComplex) transfer asynchronously. dir: +1 forward, -1 inverse.
+func FFTBatch(x []complex128, n int, dir int) []complex128 {
+	if n <= 0 || len(x)%n != 0 {
+		panic("FFTBatch: len(x) must be a multiple of n")
+	}
+	r := make([]complex128, len(x))
+	if len(x) == 0 {
+		return r
+	}
+	check(C.gd_fft_batch_c2c(cptr(x), cptr(r), C.int64_t(n), C.int64_t(len(x)/n), C.int(dir)), "gd_fft_batch_c2c")
+	return r
+}
+
+// PinnedComplex returns a slice of n complex128 in page-locked host memory (free it with FreePinned).
+func PinnedComplex(n int) []complex128 {
+	p := C.gd_pinned_alloc(C.size_t(n) * 16)
+	if p == nil {
+		panic("gd_pinned_alloc: " + C.GoString(C.gd_last_error()))
+	}
+	return unsafe.Slice((*complex128)(p), n)
+}
+
+// FreePinned releases a slice obtained from PinnedComplex.
+func FreePinned(x []complex128) {
+	if len(x) > 0 {
+		C.gd_pinned_free(unsafe.Pointer(&x[0]))
+	}
+}
+
 var worker_pool_size = 0
 
 // SetWorkerPoolSize is kept for API compatibility; the GPU path has no worker pool.

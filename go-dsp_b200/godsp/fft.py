@@ -63,6 +63,18 @@ def FFTN(m): return _fftn(m, 1)                 # fft/fft.go:157
 def IFFTN(m): return _fftn(m, -1)               # fft/fft.go:162
 
 
+def FFTBatch(x, n, direction=1):
+    """Additive batched call (go/fft/fft_b200.go FFTBatch): len(x)/n transforms back to back."""
+    from . import _capi
+    x = _c(x).reshape(-1)
+    if n <= 0 or x.shape[0] % n:
+        raise _host.GoPanic("FFTBatch: len(x) must be a multiple of n")
+    out = np.empty_like(x)
+    if x.shape[0]:
+        _capi.check(_capi.lib().gd_fft_batch_c2c(x.ctypes.data, out.ctypes.data, n, x.shape[0] // n, direction))
+    return out
+
+
 def SetWorkerPoolSize(n): _host.lib().gdh_set_worker_pool_size(int(n))          # fft/fft.go:95 (no effect on the GPU)
 def EnsureRadix2Factors(n): _host.check(_host.lib().gdh_ensure_radix2_factors(int(n)))   # fft/radix2.go:35
 def reverseBits(v, s): return int(_host.lib().gdh_reverse_bits(int(v), int(s)))  # fft/radix2.go:184

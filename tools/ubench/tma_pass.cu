@@ -159,6 +159,10 @@ int main(int argc, char** argv) {
         f.dbg_nop1st = getenv("TMA_NOP1ST") ? 1 : 0;
         f.dbg_nop2st = getenv("TMA_NOP2ST") ? 1 : 0;
         f.two_queues = getenv("TMA_2Q") ? atoi(getenv("TMA_2Q")) : 0;
+        f.dbg_acqload = getenv("TMA_ACQLOAD") ? 1 : 0;
+        f.dbg_nopubfence = getenv("TMA_NOPUBFENCE") ? 1 : 0;
+        f.dbg_out_alias = getenv("TMA_OUTALIAS") ? ~1 : 0;
+        f.dbg_in_alias = getenv("TMA_INALIAS") ? ~1 : 0;
         f.dbg_noload = getenv("TMA_NOLOAD") ? 1 : 0;
         CK(cudaMemsetAsync(out, 0, nbuf * N * 16, st));
         float fb = 1e9;
