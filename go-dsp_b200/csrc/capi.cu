@@ -150,6 +150,7 @@ int gd_set_option(const char* key, int64_t value) {
     else if (!strcmp(key, "tma")) d.use_tma = value != 0;
     else if (!strcmp(key, "tma_two_queues")) { if (value < 0 || value > 4) return (int)invalid_arg("tma_two_queues out of range"); d.tma_two_queues = (int)value; }
     else if (!strcmp(key, "tma_dbg")) d.tma_dbg = (int)value;
+    else if (!strcmp(key, "tma_p1_bulk")) d.tma_p1_bulk = value != 0;
     else if (!strcmp(key, "tma_delay")) { if (value < 0 || value > 4) return (int)invalid_arg("tma_delay out of range"); d.tma_delay = (int)value; }
     else if (!strcmp(key, "tiled_scratch")) d.tiled_scratch = value != 0;
     else if (!strcmp(key, "l2_window")) d.use_l2_window = value != 0;

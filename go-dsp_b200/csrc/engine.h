@@ -91,6 +91,7 @@ struct Device {
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)
     int tma_two_queues = 0;              // separate in-order queues for pass-1 / pass-2 tiles (measured slower: the P1/P2 mix per SM drifts)
+    bool tma_p1_bulk = true;             // pass-1 output through the async proxy (staged bulk stores, published on completion)
     int tma_dbg = 0;                     // bisecting switches of the fused kernel (bit 0: acquire load instead of fence, bit 1: unsplit drain, bit 2: no fence by the storing warps, bit 3: writer-side proxy fence)
     int tma_delay = 1;                   // phases between P1(g) and P2(g); delay + 2 slots of 16 MiB must stay in L2
     std::recursive_mutex mu;             // every public entry point locks its device

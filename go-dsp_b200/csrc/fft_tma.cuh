@@ -95,6 +95,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int 
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];\n"
                  ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)) : "memory");
 }
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* ssrc, unsigned bytes) {   // contiguous shared -> global
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d_hint(void* gdst, const void* ssrc, unsigned bytes, unsigned long long pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n"
+                 ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
@@ -644,7 +651,12 @@ fft_tma_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 //   log[32] item ids by local step, log_count (monotonic, written by the loader) for the helper warps
 constexpr int TMA2_HALF_BYTES = TMA_TILE_BYTES / 2;          // 32768
 constexpr int TMA2_NSLOT = 3;
-constexpr int TMA2_SMEM = TMA2_NSLOT * TMA2_HALF_BYTES + 2 * TMA_TILE_BYTES + 1024;   // 230400
+// a work buffer also stages pass-1 output as 4 rows of 1024 + 2 elements (P1BULK; the 32-byte skew makes the 4-lines x
+// 2-residues store pattern conflict-free): 65664 bytes, a multiple of 128
+constexpr int TMA2_ROWLINE = TMA_L + 2;
+constexpr int TMA2_WBYTES = TMA_T * TMA2_ROWLINE * 16;
+constexpr int TMA2_WELEMS = TMA2_WBYTES / 16;
+constexpr int TMA2_SMEM = TMA2_NSLOT * TMA2_HALF_BYTES + 2 * TMA2_WBYTES + 1024;      // 230656
 
 __device__ __forceinline__ int ld_volatile_shared(const volatile int* p) { return *p; }
 
@@ -665,13 +677,17 @@ __device__ __forceinline__ TmaItem tma_decode2(int code) {
     return it;
 }
 
+// P1BULK: pass-1 output is staged in the work buffer too and leaves through the async proxy (four 16 KiB bulk copies, one per
+// row of Int); the storer lane of the group publishes the tile after cp.async.bulk.wait_group 0, i.e. when the writes are
+// complete -- no device-scope fence by the four storing warps, no publisher lane.
+template <bool P1BULK>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_int,
                       const __grid_constant__ CUtensorMap tm_out, const TmaFusedParams a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     cpx* land = reinterpret_cast<cpx*>(smem_raw);
     cpx* work = reinterpret_cast<cpx*>(smem_raw + TMA2_NSLOT * TMA2_HALF_BYTES);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + TMA2_NSLOT * TMA2_HALF_BYTES + 2 * TMA_TILE_BYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + TMA2_NSLOT * TMA2_HALF_BYTES + 2 * TMA2_WBYTES);
     // full_h is per (slot, consumer group): a parity wait is only safe for a waiter that observes EVERY phase of its
     // barrier in order. With one barrier per slot, group B could reach its wait for phase k+1 while phase k -- a half
     // of group A's tile, issued earlier but landing later (HBM vs L2) -- was still open; the parity test then
@@ -686,7 +702,7 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     volatile int* log_count = reinterpret_cast<volatile int*>(bars + 38);  // local steps published by the loader
     constexpr int TPT = TMA_L / TMA_T;
     constexpr int HALF_ELEMS = TMA2_HALF_BYTES / 16;       // 2048
-    constexpr int TILE_ELEMS = TMA_TILE_BYTES / 16;        // 4096
+    constexpr int TILE_ELEMS = TMA2_WELEMS;                // work buffer pitch (4104 elements)
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
@@ -815,7 +831,56 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                                     (2 * h + j) * TMA_BOX_ROWS, (w.type == 0 ? tfc & ~a.dbg_in_alias : tfc), fb);
                 }
             }
-        } else if (tid == 2 * TMA_GROUP + 32) {
+        } else if (P1BULK && (tid == 2 * TMA_GROUP + 32 || tid == 2 * TMA_GROUP + 64)) {
+            // ------------------------------------------------------------ P1BULK: one storer lane per consumer group, every tile
+            const int g = tid == 2 * TMA_GROUP + 32 ? 0 : 1;
+            const unsigned long long pol_last = policy_evict_last();
+            unsigned ns = 0;
+            for (int it = g;; it += 2) {
+                while (ld_volatile_shared(log_count) <= it) __nanosleep(64);
+                __threadfence_block();
+                const int item = log[it & 31];
+                if (item < 0) break;
+                const TmaItem pi = a.two_queues ? tma_decode2(item) : tma_decode(item, B, D);
+                mbar_wait(staged + g, ns & 1);
+                ns++;
+                const cpx* srcb = work + (size_t)g * TILE_ELEMS;
+                if (pi.type == 1) {
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                        tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T);
+                    tma_commit();
+#pragma unroll
+                    for (int j = 2; j < 4; j++)
+                        tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T);
+                    tma_commit();
+                } else {
+                    cpx* dst = a.scratch + (size_t)(pi.tf % S) * ((size_t)TMA_L * TMA_L) + (size_t)(pi.c * TMA_T) * TMA_L;
+#pragma unroll
+                    for (int l = 0; l < 2; l++) {
+                        if (a.hints) bulk_store_1d_hint(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16, pol_last);
+                        else bulk_store_1d(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16);
+                    }
+                    tma_commit();
+#pragma unroll
+                    for (int l = 2; l < 4; l++) {
+                        if (a.hints) bulk_store_1d_hint(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16, pol_last);
+                        else bulk_store_1d(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16);
+                    }
+                    tma_commit();
+                }
+                asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+                mbar_arrive(drained + 2 * g);
+                tma_wait_read0();
+                mbar_arrive(drained + 2 * g + 1);
+                if (pi.type == 0) {
+                    tma_wait_all0();                                   // the four rows of Int are written
+                    asm volatile("fence.proxy.async.global;\n" ::: "memory");
+                    red_release_gpu(a.done1 + pi.tf, 1);
+                }
+            }
+            tma_wait_all0();
+        } else if (!P1BULK && tid == 2 * TMA_GROUP + 32) {
             // ------------------------------------------------------------ storer of P2 tiles
             unsigned np2[2] = {0, 0};
             for (int it = 0;; it++) {
@@ -848,7 +913,7 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 mbar_arrive(drained + 2 * g + 1);
             }
             tma_wait_all0();
-        } else if (tid == 2 * TMA_GROUP + 64) {
+        } else if (!P1BULK && tid == 2 * TMA_GROUP + 64) {
             // ------------------------------------------------------------ publisher of P1 tiles
             unsigned np1[2] = {0, 0};
             for (int it = 0;; it++) {
@@ -939,7 +1004,18 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         asm volatile("" : "+d"(w.x), "+d"(w.y));
         mul_powers32(x, w);
         dft32(x);
-        if (wi.type == 0) {
+        if (wi.type == 0 && P1BULK) {
+            mul_geometric32(x, cmul(t_hi0, t_lo0), cmul(t_hi1, t_lo1));
+            mbar_wait(rd + g, nrd & 1);                      // every gather of this tile is done: the buffer may be overwritten
+            nrd++;
+            cpx* s = wbuf + ell * TMA2_ROWLINE + p;          // Int[n2 = 4c + ell][k1 = p + 32 r], rows skewed by 2 elements
+#pragma unroll
+            for (int r = 0; r < 32; r++) s[r * 32] = x[r];
+            fence_proxy_async();
+            mbar_arrive(staged + g);
+            np2++;
+            prev_p2 = true;
+        } else if (wi.type == 0) {
             cpx* dst = a.scratch + (size_t)(wi.tf % S) * ((size_t)TMA_L * TMA_L) + (size_t)(wi.c * TMA_T + ell) * TMA_L + p;
             const cpx t0 = cmul(t_hi0, t_lo0), s1c = cmul(t_hi1, t_lo1);
             const cpx s2 = csqr(s1c), s4 = csqr(s2);

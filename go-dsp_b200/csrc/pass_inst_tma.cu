@@ -51,7 +51,8 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
                     int st_conj, double scale, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        GD_CUDA(cudaFuncSetAttribute(fft_tma_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
+        GD_CUDA(cudaFuncSetAttribute(fft_tma_fused2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
+        GD_CUDA(cudaFuncSetAttribute(fft_tma_fused2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
         attr_set = true;
     }
     TmaEncodeFn enc;
@@ -100,12 +101,14 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
         f.wl = d.wl[10]; f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.tw_log2m = 20;
         f.ld_conj = ld_conj; f.st_conj = st_conj; f.scale = scale;
         f.two_queues = d.tma_two_queues;
+        f.hints = d.tma_p1_bulk ? 1 : 0;        // evict-last on the bulk stores of Int: without it they crawl under the persisting window
         f.dbg_acqload = d.tma_dbg & 1; f.dbg_nosplit = (d.tma_dbg >> 1) & 1; f.dbg_nopubfence = (d.tma_dbg >> 2) & 1; f.dbg_wproxy = (d.tma_dbg >> 3) & 1;
         cudaError_t e = cudaMemsetAsync(cnt, 0, (2 * (size_t)CH + 2) * sizeof(int), st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(counters)"); break; }
         const long long nitems = 2 * nb * (TMA_L / TMA_T);
         const int grid = (int)(nitems < d.num_sms ? nitems : d.num_sms);
-        fft_tma_fused2_kernel<<<grid, TMA_THREADS, TMA2_SMEM, st>>>(m_x, m_int, m_out, f);
+        if (d.tma_p1_bulk) fft_tma_fused2_kernel<true><<<grid, TMA_THREADS, TMA2_SMEM, st>>>(m_x, m_int, m_out, f);
+        else fft_tma_fused2_kernel<false><<<grid, TMA_THREADS, TMA2_SMEM, st>>>(m_x, m_int, m_out, f);
         e = cudaGetLastError();
         if (e != cudaSuccess) { rc = cuda_fail(e, "fft_tma_fused_kernel launch"); break; }
         g_launches++;

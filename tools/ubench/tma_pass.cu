@@ -130,7 +130,8 @@ int main(int argc, char** argv) {
         CUtensorMap ms = make_map(enc, scratch, S, N, getenv("TMA_PROMO_INT") ? atoi(getenv("TMA_PROMO_INT")) : 0);
         mx = make_map(enc, x, nbuf, N, promo);
         CK(cudaFuncSetAttribute(fft_tma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
-        CK(cudaFuncSetAttribute(fft_tma_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
+        CK(cudaFuncSetAttribute(fft_tma_fused2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
+        CK(cudaFuncSetAttribute(fft_tma_fused2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
         cudaStream_t st; CK(cudaStreamCreate(&st));
         if (persist) {
             int maxp = 0, maxw = 0;
@@ -169,7 +170,8 @@ int main(int argc, char** argv) {
         for (int i = 0; i < iters + 1; i++) {
             CK(cudaMemsetAsync(cnt, 0, (2 * batch + 2) * sizeof(int), st));
             cudaEventRecord(e0, st);
-            if (fused == 2) fft_tma_fused2_kernel<<<grid, TMA_THREADS, TMA2_SMEM, st>>>(mx, ms, mo, f);
+            if (fused == 3) fft_tma_fused2_kernel<true><<<grid, TMA_THREADS, TMA2_SMEM, st>>>(mx, ms, mo, f);
+            else if (fused == 2) fft_tma_fused2_kernel<false><<<grid, TMA_THREADS, TMA2_SMEM, st>>>(mx, ms, mo, f);
             else fft_tma_fused_kernel<<<grid, TMA_THREADS, TMA_SMEM, st>>>(mx, ms, mo, f);
             cudaEventRecord(e1, st);
             CK(cudaStreamSynchronize(st));
