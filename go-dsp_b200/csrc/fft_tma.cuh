@@ -294,7 +294,8 @@ struct TmaFusedParams {
     int ld_conj, st_conj;
     double scale;
     long long* stats;            // optional [gridDim.x][8] cycle counters (tools/ubench/tma_pass.cu); null in the product
-    int hints;                   // L2 eviction-priority hints on the TMA traffic
+    int hints;                   // L2 eviction-priority hints: 1 = Int bulk stores evict-last, 2 = x loads evict-first,
+                                 // 4 = Int loads evict-last, 8 = output stores evict-first
     int p2_stg;                  // pass 2 stores straight from registers (64-byte chunks) instead of staging a TMA store:
                                  // the tile buffer is free again right after the gather
     cpx* out;                    // p2_stg: output base, transform tf at out + tf * out_dist
@@ -723,6 +724,7 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         if (tid == 2 * TMA_GROUP) {
             // ------------------------------------------------------------ loader
             int tokens = 0, ready_tf = -1;
+            const unsigned long long ld_pol_first = policy_evict_first(), ld_pol_last = policy_evict_last();
             long long hidx = 0;                             // halves issued so far
             int ready_tf2 = -1, free_tf1 = S - 1;       // transforms known to be published / whose slot is known to be free
             const int ntiles = B * TPT;
@@ -825,16 +827,25 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     unsigned long long* fb = full_h + 2 * s + (it & 1);
                     if (a.dbg_noload) { mbar_arrive(fb); continue; }
                     mbar_expect_tx(fb, TMA2_HALF_BYTES);
+                    const int hint_bit = w.type == 0 ? 2 : 4;
+                    if (a.hints & hint_bit) {
+                        const unsigned long long pol = w.type == 0 ? ld_pol_first : ld_pol_last;
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+                            tma_load_3d_hint(land + (size_t)s * HALF_ELEMS + j * TMA_BOX_ROWS * TMA_T, tm, w.c * 2 * TMA_T,
+                                             (2 * h + j) * TMA_BOX_ROWS, tfc, fb, pol);
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 2; j++)
                         tma_load_3d(land + (size_t)s * HALF_ELEMS + j * TMA_BOX_ROWS * TMA_T, tm, w.c * 2 * TMA_T,
                                     (2 * h + j) * TMA_BOX_ROWS, (w.type == 0 ? tfc & ~a.dbg_in_alias : tfc), fb);
+                    }
                 }
             }
         } else if (P1BULK && (tid == 2 * TMA_GROUP + 32 || tid == 2 * TMA_GROUP + 64)) {
             // ------------------------------------------------------------ P1BULK: one storer lane per consumer group, every tile
             const int g = tid == 2 * TMA_GROUP + 32 ? 0 : 1;
-            const unsigned long long pol_last = policy_evict_last();
+            const unsigned long long pol_last = policy_evict_last(), pol_first = policy_evict_first();
             unsigned ns = 0;
             for (int it = g;; it += 2) {
                 while (ld_volatile_shared(log_count) <= it) __nanosleep(64);
@@ -846,6 +857,16 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 ns++;
                 const cpx* srcb = work + (size_t)g * TILE_ELEMS;
                 if (pi.type == 1) {
+                    if (a.hints & 8) {
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+                            tma_store_3d_hint(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T, pol_first);
+                        tma_commit();
+#pragma unroll
+                        for (int j = 2; j < 4; j++)
+                            tma_store_3d_hint(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T, pol_first);
+                        tma_commit();
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 2; j++)
                         tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T);
@@ -854,17 +875,18 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     for (int j = 2; j < 4; j++)
                         tma_store_3d(&tm_out, pi.c * 2 * TMA_T, j * TMA_BOX_ROWS, pi.tf, srcb + j * TMA_BOX_ROWS * TMA_T);
                     tma_commit();
+                    }
                 } else {
                     cpx* dst = a.scratch + (size_t)(pi.tf % S) * ((size_t)TMA_L * TMA_L) + (size_t)(pi.c * TMA_T) * TMA_L;
 #pragma unroll
                     for (int l = 0; l < 2; l++) {
-                        if (a.hints) bulk_store_1d_hint(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16, pol_last);
+                        if (a.hints & 1) bulk_store_1d_hint(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16, pol_last);
                         else bulk_store_1d(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16);
                     }
                     tma_commit();
 #pragma unroll
                     for (int l = 2; l < 4; l++) {
-                        if (a.hints) bulk_store_1d_hint(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16, pol_last);
+                        if (a.hints & 1) bulk_store_1d_hint(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16, pol_last);
                         else bulk_store_1d(dst + (size_t)l * TMA_L, srcb + l * TMA2_ROWLINE, TMA_L * 16);
                     }
                     tma_commit();
