@@ -363,6 +363,9 @@ def run_ours(args):
         if world > 1:
             line["fft_1d_sharded"] = run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed)
             line["gpu_launches"] += line["fft_1d_sharded"].pop("_launches")
+            px = line["fft_1d_sharded"].pop("_peer", None)
+            if px is not None:
+                px.close()
 
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -420,19 +423,26 @@ def run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed):
     capi.check(L.gd_fill_splitmix_dev(src.data_ptr(), 2 * n1 * w, 6, 2 * rank * n1 * w, sp))
     steps, warmup = max(2, min(args.steps, 3)), max(1, min(args.warmup, 2))
 
-    def step():
+    def step_nccl():
         slab.copy_(src)
         D.fft_1d_sharded(slab, n, ops, work=work)
+    ms_nccl, _, _ = timed(step_nccl, steps, warmup)
+    px = D.PeerExchange(n1 * w, ops)
+
+    def step():
+        slab.copy_(src)
+        D.fft_1d_sharded(slab, n, ops, work=work, peer=px)
     ms, launches, clocks = timed(step, steps, warmup)
     # Parseval on the last step: sum |X|^2 = n * sum |x|^2 over all ranks
     e = torch.stack([(work.real ** 2 + work.imag ** 2).sum(), (src.real ** 2 + src.imag ** 2).sum()])
     dist.all_reduce(e)
     return {"metric": "single 1-D FFT GS/s (complex128, 2^%d points over %d GPUs)" % (lg, world), "value": n / (ms * 1e-3) / 1e9,
             "unit": "GS/s", "ms_per_step": ms, "scaling": "weak", "log2n": lg,
-            "api": "godsp.distributed.fft_1d_sharded: strided lines, twiddle, NCCL all-to-all, transpose, strided lines (+ one device copy of the slab per step)",
+            "api": "godsp.distributed.fft_1d_sharded(peer=PeerExchange): strided lines, ONE kernel for twiddle + transpose + NVLink P2P stores into the peers' buffers (gd_fourstep_exchange_dev), strided lines (+ one device copy of the slab per step)",
+            "nccl_all_to_all_variant_ms": ms_nccl,
             "all_to_all_bytes_per_gpu": 16 * (n // world) * (world - 1) // world,
             "parseval_rel_err": abs(float(e[0].item()) / (n * float(e[1].item())) - 1.0),
-            "clocks": clocks, "_launches": int(launches)}
+            "clocks": clocks, "_launches": int(launches), "_peer": px}
 
 
 def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_host, skip, hbm_peak, peak_src):

@@ -388,6 +388,38 @@ int gd_repack_gkw_dev(const double* in, double* out, int64_t g, int64_t k, int64
     GD_ENTER();
     return (int)repack_gkw((const cpx*)in, (cpx*)out, g, k, w, pick(d, stream));
 }
+int gd_ipc_alloc(void** p, size_t bytes, unsigned char* handle64) {
+    if (!p || !handle64 || bytes == 0) return (int)invalid_arg("gd_ipc_alloc: bad arguments");
+    GD_ENTER();
+    (void)d;
+    GD_CUDA(cudaMalloc(p, bytes));
+    cudaIpcMemHandle_t hnd;
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    GD_CUDA(cudaIpcGetMemHandle(&hnd, *p));
+    memcpy(handle64, &hnd, 64);
+    return ::gd::GD_OK;
+}
+int gd_ipc_open(const unsigned char* handle64, void** p) {
+    if (!p || !handle64) return (int)invalid_arg("gd_ipc_open: bad arguments");
+    GD_ENTER();
+    (void)d;
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle64, 64);
+    GD_CUDA(cudaIpcOpenMemHandle(p, hnd, cudaIpcMemLazyEnablePeerAccess));
+    return ::gd::GD_OK;
+}
+int gd_ipc_close(void* p) {
+    GD_ENTER();
+    (void)d;
+    GD_CUDA(cudaIpcCloseMemHandle(p));
+    return ::gd::GD_OK;
+}
+int gd_fourstep_exchange_dev(const double* slab, void* const* peer_recv, int64_t n1, int64_t w, int rank, int world, int log2n,
+                             void* stream) {
+    if (!slab || !peer_recv) return (int)invalid_arg("fourstep_exchange_dev: null");
+    GD_ENTER();
+    return (int)fourstep_exchange((const cpx*)slab, (cpx* const*)peer_recv, n1, w, rank, world, log2n, pick(d, stream));
+}
 int gd_transpose_batched_dev(const double* in, double* out, int64_t batch, int64_t rows, int64_t cols, void* stream) {
     if (!in || !out) return (int)invalid_arg("transpose_batched_dev: null");
     GD_ENTER();

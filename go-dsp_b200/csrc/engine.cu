@@ -421,6 +421,60 @@ Status transpose_batched(const cpx* in, cpx* out, long long batch, long long row
     return GD_OK;
 }
 
+// The exchange step of the sharded four-step as ONE kernel over peer memory (NVLink P2P stores) instead of
+// twiddle kernel + NCCL all-to-all + transpose kernel: block (h, k-tile, c-tile) reads slab[h*K + k][c] (this rank's
+// [N1][W] slab after the length-N1 lines), multiplies by w_N^((h*K + k) * (g*W + c)), transposes the 64 x 32 tile
+// through shared memory and stores it straight into rank h's receive buffer at [g*W + c][k] (rows of K elements,
+// 1 KiB contiguous per row segment). One HBM read + one NVLink write per element; the receive buffer is then
+// already [N2][K], ready for the length-N2 lines.
+struct PeerPtrs { cpx* p[16]; };
+__global__ void __launch_bounds__(256) fourstep_exchange_kernel(const cpx* __restrict__ slab, PeerPtrs peers, long long K,
+                                                                long long W, int g, int log2n) {
+    __shared__ cpx tile[64][33];
+    const int h = blockIdx.z;
+    const long long k0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long c = c0 + tx;
+    if (c < W) {
+        const unsigned long long mask = (1ULL << log2n) - 1ULL, n2 = (unsigned long long)g * W + c;
+        const double invn = 1.0 / (double)(1ULL << log2n);
+        const unsigned long long k1a = (unsigned long long)h * K + k0 + ty;
+        double sn, cs;
+        sincospi(-2.0 * (double)((k1a * n2) & mask) * invn, &sn, &cs);
+        cpx w = make_double2(cs, sn);
+        sincospi(-2.0 * (double)((8ULL * n2) & mask) * invn, &sn, &cs);
+        const cpx step = make_double2(cs, sn);
+        const cpx* src = slab + ((long long)h * K + k0 + ty) * W + c;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (k0 + ty + 8 * i < K) tile[ty + 8 * i][tx] = cmul(src[(long long)(8 * i) * W], w);
+            w = cmul(w, step);
+        }
+    }
+    __syncthreads();
+    cpx* dst = peers.p[h] + ((long long)g * W + c0) * K + k0;
+    for (int rr = ty; rr < 32; rr += 8) {
+        if (c0 + rr >= W) break;
+#pragma unroll
+        for (int kk = tx; kk < 64; kk += 32)
+            if (k0 + kk < K) dst[(long long)rr * K + kk] = tile[kk][rr];
+    }
+}
+Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,
+                         cudaStream_t st) {
+    if (!slab || !peer_recv || world < 1 || world > 16 || rank < 0 || rank >= world || n1 % world || w < 1 || log2n < 1 || log2n > 40)
+        return invalid("fourstep_exchange: bad arguments");
+    const long long K = n1 / world;
+    PeerPtrs pp;
+    for (int i = 0; i < 16; i++) pp.p[i] = i < world ? peer_recv[i] : nullptr;
+    const long long gx = (w + 31) / 32, gy = (K + 63) / 64;
+    if (gy > 65535) return invalid("fourstep_exchange: grid too large");
+    fourstep_exchange_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)world), 256, 0, st>>>(slab, pp, K, w, rank, log2n);
+    g_launches++;
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
 Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st) {
     if (rows < 1 || cols < 1 || log2n < 1 || log2n > 40) return invalid("fourstep_twiddle: bad arguments");
     long long threads = rows * ((cols + 15) / 16);

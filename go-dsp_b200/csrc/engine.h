@@ -129,6 +129,8 @@ Status pwelch_finalize(const double* raw, long long lp, long long nsegs, double 
 // ---- distributed four-step (C5) building blocks -------------------------------------------
 Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st);
 Status repack_gkw(const cpx* in, cpx* out, long long G, long long K, long long W, cudaStream_t st);
+Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,
+                         cudaStream_t st);
 Status transpose_batched(const cpx* in, cpx* out, long long batch, long long rows, long long cols, cudaStream_t st);
 // strided lines: `outer` blocks of `len` lines-elements with element stride s (fft_axis)
 Status fft_strided(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st);

@@ -36,6 +36,9 @@ SIGNATURES = {
     "gd_fft_strided_c2c_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "gd_fourstep_twiddle_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp]),
     "gd_repack_gkw_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
+    "gd_fourstep_exchange_dev": (_int, [_vp, C.POINTER(_vp), _i64, _i64, _int, _int, _int, _vp]),
+    "gd_ipc_alloc": (_int, [C.POINTER(_vp), _sz, C.c_char_p]), "gd_ipc_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
+    "gd_ipc_close": (_int, [_vp]),
     "gd_transpose_batched_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "gd_pwelch_partial_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "gd_pwelch_finalize_dev": (_int, [_vp, _i64, _i64, C.c_double, _vp, _vp]),

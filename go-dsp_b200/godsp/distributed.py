@@ -73,6 +73,58 @@ class DeviceOps:
         _capi.check(self.L.gd_transpose_batched_dev(src.data_ptr(), dst.data_ptr(), batch, rows, cols, self._sp()))
 
 
+class _DevArray:
+    """A raw device pointer as a CUDA-array-interface object (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, nelem):
+        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<c16", "data": (ptr, False), "version": 3, "strides": None}
+
+
+class PeerExchange:
+    """Receive buffers of all ranks mapped into this process (CUDA IPC), for the fused exchange kernel
+    (`gd_fourstep_exchange_dev`: twiddle + transpose + NVLink P2P stores in one pass, no NCCL data movement).
+    One instance per (group, slab size); collective to construct and to close."""
+
+    def __init__(self, nelem, ops, group=None):
+        self.L, self.ops, self.group = ops.L, ops, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _capi.check(self.L.gd_ipc_alloc(C.byref(own), nelem * 16, handle))
+        self.own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ptrs, self.opened = [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.own)
+            else:
+                p = C.c_void_p()
+                _capi.check(self.L.gd_ipc_open(C.c_char_p(h), C.byref(p)))
+                self.ptrs.append(p.value)
+                self.opened.append(p.value)
+        self.ptr_array = (C.c_void_p * self.world)(*self.ptrs)
+        self.recv = torch.as_tensor(_DevArray(self.own, nelem), device=ops.device)
+        self.token = torch.zeros(1, device=ops.device)
+
+    def fence(self):
+        """stream-ordered rendezvous of all ranks (a 1-element all-reduce): nobody passes before everybody's kernels
+        enqueued so far are done"""
+        dist.all_reduce(self.token, group=self.group)
+
+    def exchange(self, slab, n1, w, log2n):
+        _capi.check(self.L.gd_fourstep_exchange_dev(slab.data_ptr(), self.ptr_array, n1, w, self.rank, self.world, log2n, self.ops._sp()))
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for p in self.opened:
+            _capi.check(self.L.gd_ipc_close(p))
+        self.opened = []
+        del self.recv
+        _capi.check(self.L.gd_dev_free(self.own))
+
+
 def _all_to_all(recv, send, group):
     # equal contiguous splits; complex128 travels as pairs of float64
     dist.all_to_all_single(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), group=group)
@@ -88,13 +140,23 @@ def split_1d(n, world):
     return n1, n2, n1 // world, n2 // world
 
 
-def fft_1d_sharded(slab, n, ops, group=None, work=None):
+def fft_1d_sharded(slab, n, ops, group=None, work=None, peer=None):
     """Forward transform of one n-point signal.  `slab`: this rank's [N1][W] column slab (flattened, overwritten).
-    Returns this rank's [N2][K] slab of the spectrum (a new tensor, or `work` if given: n/world elements)."""
+    Returns this rank's [N2][K] slab of the spectrum (a new tensor, or `work` if given: n/world elements).
+    peer: a PeerExchange of n/world elements -> the exchange step is ONE kernel storing into the peers' buffers over
+    NVLink (twiddle + transpose fused in); otherwise twiddle kernel + NCCL all-to-all + transpose kernel."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n1, n2, k, w = split_1d(n, world)
     if slab.numel() != n1 * w:
         raise ValueError("slab has %d elements, expected %d" % (slab.numel(), n1 * w))
+    if peer is not None:
+        out = work if work is not None else ops.empty(n1 * w)
+        ops.fft_strided(slab, slab, 1, n1, w, 1)          # lines over n1
+        peer.fence()                                      # every rank is done reading its receive buffer (previous call)
+        peer.exchange(slab, n1, w, _ilog2(n))             # peer h gets [rank*W + c][k] <- slab[h*K + k][c] * w_N^(k1 n2)
+        peer.fence()                                      # every rank's stores have landed
+        ops.fft_strided(peer.recv, out, 1, n2, k, 1)      # lines over n2
+        return out
     recv = work if work is not None else ops.empty(n1 * w)
     # 1. lines over n1 (length N1, element stride W), in place
     ops.fft_strided(slab, slab, 1, n1, w, 1)

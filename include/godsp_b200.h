@@ -117,6 +117,17 @@ GD_API int gd_fourstep_twiddle_dev(double* blk_dev, int64_t rows, int64_t cols, 
 GD_API int gd_repack_gkw_dev(const double* in_dev, double* out_dev, int64_t g, int64_t k, int64_t w, void* stream);
 /* in[batch][rows][cols] -> out[batch][cols][rows] (complex128): per-source-rank transpose of the all-to-all receive buffer */
 GD_API int gd_transpose_batched_dev(const double* in_dev, double* out_dev, int64_t batch, int64_t rows, int64_t cols, void* stream);
+/* The exchange step as one kernel over peer memory (NVLink P2P stores) instead of twiddle + all-to-all + transpose:
+ * slab = this rank's [n1][w] block after the length-n1 lines; element (k1, c) times w_N^(k1 * (rank*w + c)) is stored
+ * into peer_recv[k1 / (n1/world)] at [rank*w + c][k1 % (n1/world)] (rows of n1/world elements). peer_recv: host array of
+ * `world` device pointers (own buffer at index `rank`, the others opened with gd_ipc_open). The caller orders the
+ * ranks around it (a stream-ordered collective before and after). */
+GD_API int gd_fourstep_exchange_dev(const double* slab_dev, void* const* peer_recv, int64_t n1, int64_t w, int rank, int world,
+                                    int log2n, void* stream);
+/* cudaMalloc'ed buffer + its 64-byte CUDA IPC handle; open / close a peer's handle in this process */
+GD_API int gd_ipc_alloc(void** p, size_t bytes, unsigned char* handle64);
+GD_API int gd_ipc_open(const unsigned char* handle64, void** p);
+GD_API int gd_ipc_close(void* p);
 /* raw[j] = sum over segments seg0..seg0+nseg-1 of |FFT(win * segment)[j]|^2, j < lp (one GPU's share) */
 GD_API int gd_pwelch_partial_dev(const double* x_dev, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
                           int64_t seg0, int64_t nseg, const double* win_dev, double* raw_dev, void* stream);

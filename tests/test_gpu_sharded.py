@@ -37,13 +37,22 @@ def _worker(rank, world, port, log2n, rows, cols, out):
     slab = D.scatter_signal(x, n, rank, world).cuda()
     spec = D.fft_1d_sharded(slab, n, ops)
     torch.cuda.synchronize()
+    # the same transform with the exchange step as one kernel over peer memory (CUDA IPC + NVLink stores)
+    px = D.PeerExchange(n // world, ops)
+    slab2 = D.scatter_signal(x, n, rank, world).cuda()
+    spec_p = D.fft_1d_sharded(slab2, n, ops, peer=px).clone()
+    slab2 = D.scatter_signal(x, n, rank, world).cuda()
+    spec_p2 = D.fft_1d_sharded(slab2, n, ops, peer=px).clone()     # buffer reuse across calls
+    torch.cuda.synchronize()
+    assert torch.equal(spec_p, spec_p2)
+    px.close()
     m = oracle.splitmix_complex(rows * cols, 4).reshape(rows, cols)
     rg = rows // world
     blk = torch.from_numpy(m[rank * rg:(rank + 1) * rg].copy().reshape(-1)).cuda()
     res = D.fft2_sharded(blk, rows, cols, ops)
     back = D.fft2_sharded(res.clone(), rows, cols, ops, direction=-1)
     torch.cuda.synchronize()
-    out[rank] = (spec.cpu().numpy(), res.cpu().numpy(), back.cpu().numpy())
+    out[rank] = (spec.cpu().numpy(), res.cpu().numpy(), back.cpu().numpy(), spec_p.cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,7 +66,10 @@ def _run(world, log2n, rows, cols):
     mp.spawn(_worker, args=(world, _free_port(), log2n, rows, cols, out), nprocs=world, join=True)
     n = 1 << log2n
     spec = D.gather_spectrum([torch.from_numpy(out[r][0]) for r in range(world)], n).numpy()
-    assert rel_l2(spec, oracle.fft(oracle.splitmix_complex(n, 6))) <= TOL
+    want = oracle.fft(oracle.splitmix_complex(n, 6))
+    assert rel_l2(spec, want) <= TOL
+    spec_p = D.gather_spectrum([torch.from_numpy(out[r][3]) for r in range(world)], n).numpy()
+    assert rel_l2(spec_p, want) <= TOL
     m = oracle.splitmix_complex(rows * cols, 4).reshape(rows, cols)
     got = np.concatenate([out[r][1] for r in range(world)]).reshape(rows, cols)
     assert rel_l2(got, oracle.fft2(m)) <= TOL
