@@ -382,6 +382,7 @@ def run_fft2(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
     src = torch.empty(rg * Cc, dtype=torch.complex128, device="cuda")
     capi.check(L.gd_fill_splitmix_dev(src.data_ptr(), 2 * rg * Cc, 4, 2 * rank * rg * Cc, sp))
     steps, warmup = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
+    extra, peers = {}, None
     if world == 1:
         out = torch.empty_like(src)
         dims = (C.c_int64 * 2)(R, Cc)
@@ -392,14 +393,23 @@ def run_fft2(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
     else:
         ops = D.DeviceOps()
         blk = torch.empty(rg * Cc, dtype=torch.complex128, device="cuda")
+        res = torch.empty(rg * Cc, dtype=torch.complex128, device="cuda")
 
-        def step():
+        def step_nccl():
             blk.copy_(src)
             D.fft2_sharded(blk, R, Cc, ops)
-        api = "godsp.distributed.fft2_sharded: repack, all-to-all, column lines, all-to-all, repack, row lines (+ one device copy of the input block per step)"
+        extra["nccl_all_to_all_variant_ms"], _, _ = timed(step_nccl, steps, warmup)
+        peers = (D.PeerExchange(rg * Cc, ops), D.PeerExchange(rg * Cc, ops))
+
+        def step():
+            D.fft2_sharded(src, R, Cc, ops, peers=peers, out=res)
+        api = "godsp.distributed.fft2_sharded(peers=...): block copy into the peers' column slabs over NVLink, column lines, block copy back into the peers' row blocks, row lines (gd_peer_block_copy_dev; no NCCL data movement)"
     ms, launches, clocks = timed(step, steps, warmup)
+    if peers is not None:
+        peers[0].close()
+        peers[1].close()
     return {"metric": "FFT2 Gelem/s (complex128, 16384 x 16384)", "value": R * Cc / (ms * 1e-3) / 1e9, "unit": "Gelem/s",
-            "ms_per_step": ms, "scaling": "strong", "api": api,
+            "ms_per_step": ms, "scaling": "strong", "api": api, **extra,
             "roofline": {"bound": "hbm", "achieved": 64.0 * R * Cc / world / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": 64.0 * R * Cc / world / (ms * 1e-3) / 1e9 / hbm_peak,
                          "note": "64 B per element algorithmic: two sweeps, the 4 GiB matrix is far larger than L2 (SURVEY.md 8d)"},

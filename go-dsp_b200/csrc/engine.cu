@@ -475,6 +475,31 @@ Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, l
     return GD_OK;
 }
 
+// FFT2 on row blocks: both exchanges are strided block copies into peer memory (no repack kernels, no NCCL data
+// movement). For every peer h: dst_h[dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c], r < rows, c < cols.
+__global__ void __launch_bounds__(256) peer_block_copy_kernel(const cpx* __restrict__ src, PeerPtrs peers, long long rows, long long cols,
+                                                              long long src_step, long long src_pitch, long long dst_off, long long dst_pitch) {
+    const int h = blockIdx.z;
+    const cpx* s = src + (long long)h * src_step;
+    cpx* d = peers.p[h] + dst_off;
+    for (long long r = blockIdx.y; r < rows; r += gridDim.y)
+        for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += (long long)gridDim.x * blockDim.x)
+            d[r * dst_pitch + c] = s[r * src_pitch + c];
+}
+Status peer_block_copy(const cpx* src, cpx* const* peers, int world, long long rows, long long cols, long long src_step,
+                       long long src_pitch, long long dst_off, long long dst_pitch, cudaStream_t st) {
+    if (!src || !peers || world < 1 || world > 16 || rows < 1 || cols < 1) return invalid("peer_block_copy: bad arguments");
+    PeerPtrs pp;
+    for (int i = 0; i < 16; i++) pp.p[i] = i < world ? peers[i] : nullptr;
+    long long gx = (cols + 255) / 256;
+    if (gx > 64) gx = 64;
+    long long gy = rows < 4096 ? rows : 4096;
+    peer_block_copy_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)world), 256, 0, st>>>(src, pp, rows, cols, src_step, src_pitch, dst_off, dst_pitch);
+    g_launches++;
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
 Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st) {
     if (rows < 1 || cols < 1 || log2n < 1 || log2n > 40) return invalid("fourstep_twiddle: bad arguments");
     long long threads = rows * ((cols + 15) / 16);

@@ -115,6 +115,11 @@ class PeerExchange:
     def exchange(self, slab, n1, w, log2n):
         _capi.check(self.L.gd_fourstep_exchange_dev(slab.data_ptr(), self.ptr_array, n1, w, self.rank, self.world, log2n, self.ops._sp()))
 
+    def block_copy(self, src, rows, cols, src_step, src_pitch, dst_off, dst_pitch):
+        """every peer h: peer_buffer[h][dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c]"""
+        _capi.check(self.L.gd_peer_block_copy_dev(src.data_ptr(), self.ptr_array, self.world, rows, cols, src_step, src_pitch,
+                                                  dst_off, dst_pitch, self.ops._sp()))
+
     def close(self):
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
@@ -184,15 +189,29 @@ def gather_spectrum(slabs, n):
     return torch.cat([s.view(n2, k) for s in slabs], dim=1).contiguous().view(-1)
 
 
-def fft2_sharded(block, rows, cols, ops, group=None, direction=1):
+def fft2_sharded(block, rows, cols, ops, group=None, direction=1, peers=None, out=None):
     """fft.FFT2 / IFFT2 of a rows x cols matrix; `block` is this rank's [rows/world][cols] row block
-    (flattened complex128, overwritten).  Returns the rank's row block of the result."""
-    world = dist.get_world_size(group)
+    (flattened complex128, overwritten).  Returns the rank's row block of the result.
+    peers: (PeerExchange, PeerExchange) of rows*cols/world elements each -> both exchanges are block copies into the
+    peers' buffers over NVLink (gd_peer_block_copy_dev), no repack kernels and no NCCL data movement."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     if rows % world or cols % world:
         raise ValueError("world size %d must divide %d x %d" % (world, rows, cols))
     rg, wc = rows // world, cols // world
     if block.numel() != rg * cols:
         raise ValueError("block has %d elements, expected %d" % (block.numel(), rg * cols))
+    if peers is not None:
+        colp, rowp = peers
+        res = out if out is not None else ops.empty(rg * cols)
+        # my columns [h*wc, (h+1)*wc) of my rows -> rank h's column slab [rows][wc], rows [rank*rg, (rank+1)*rg)
+        colp.block_copy(block, rg, wc, wc, cols, rank * rg * wc, wc)
+        colp.fence()
+        ops.fft_strided(colp.recv, colp.recv, 1, rows, wc, direction)    # every column (fft/fft.go:138-144)
+        # rows [h*rg, (h+1)*rg) of my column slab -> rank h's row block [rg][cols], columns [rank*wc, (rank+1)*wc)
+        rowp.block_copy(colp.recv, rg, wc, rg * wc, wc, rank * wc, cols)
+        rowp.fence()
+        ops.fft_rows(rowp.recv, res, cols, rg, direction)                # every row (fft/fft.go:146-151)
+        return res
     tmp = ops.empty(rg * cols)
     # [rg][world][wc] -> [world][rg][wc]: destination-major send buffer
     ops.swap_leading(block, tmp, rg, world, wc)

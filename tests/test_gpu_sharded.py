@@ -52,6 +52,15 @@ def _worker(rank, world, port, log2n, rows, cols, out):
     res = D.fft2_sharded(blk, rows, cols, ops)
     back = D.fft2_sharded(res.clone(), rows, cols, ops, direction=-1)
     torch.cuda.synchronize()
+    # the same through peer memory, twice (buffer reuse)
+    pp = (D.PeerExchange(rg * cols, ops), D.PeerExchange(rg * cols, ops))
+    blk2 = torch.from_numpy(m[rank * rg:(rank + 1) * rg].copy().reshape(-1)).cuda()
+    res_p = D.fft2_sharded(blk2, rows, cols, ops, peers=pp).clone()
+    back_p = D.fft2_sharded(res_p.clone(), rows, cols, ops, direction=-1, peers=pp).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(res_p, res) and torch.equal(back_p, back)     # same kernels, same order: bit-identical
+    pp[0].close()
+    pp[1].close()
     out[rank] = (spec.cpu().numpy(), res.cpu().numpy(), back.cpu().numpy(), spec_p.cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
