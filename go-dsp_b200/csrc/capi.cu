@@ -420,11 +420,11 @@ int gd_fourstep_exchange_dev(const double* slab, void* const* peer_recv, int64_t
     GD_ENTER();
     return (int)fourstep_exchange((const cpx*)slab, (cpx* const*)peer_recv, n1, w, rank, world, log2n, pick(d, stream));
 }
-int gd_peer_block_copy_dev(const double* src, void* const* peers, int world, int64_t rows, int64_t cols, int64_t src_step,
+int gd_peer_block_copy_dev(const double* src, void* const* peers, int world, int rank, int64_t rows, int64_t cols, int64_t src_step,
                            int64_t src_pitch, int64_t dst_off, int64_t dst_pitch, void* stream) {
     if (!src || !peers) return (int)invalid_arg("peer_block_copy_dev: null");
     GD_ENTER();
-    return (int)peer_block_copy((const cpx*)src, (cpx* const*)peers, world, rows, cols, src_step, src_pitch, dst_off, dst_pitch, pick(d, stream));
+    return (int)peer_block_copy((const cpx*)src, (cpx* const*)peers, world, rank, rows, cols, src_step, src_pitch, dst_off, dst_pitch, pick(d, stream));
 }
 int gd_transpose_batched_dev(const double* in, double* out, int64_t batch, int64_t rows, int64_t cols, void* stream) {
     if (!in || !out) return (int)invalid_arg("transpose_batched_dev: null");

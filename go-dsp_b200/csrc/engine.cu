@@ -429,10 +429,13 @@ Status transpose_batched(const cpx* in, cpx* out, long long batch, long long row
 // already [N2][K], ready for the length-N2 lines.
 struct PeerPtrs { cpx* p[16]; };
 __global__ void __launch_bounds__(256) fourstep_exchange_kernel(const cpx* __restrict__ slab, PeerPtrs peers, long long K,
-                                                                long long W, int g, int log2n) {
+                                                                long long W, int g, int log2n, int world_) {
     __shared__ cpx tile[64][33];
-    const int h = blockIdx.z;
-    const long long k0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 32;
+    // consecutive blocks go to different peers, and rank g starts with peer g + 1: with one peer per grid slice every rank
+    // wrote to the same destination at the same time (8 GPUs: 56 ms against 34 ms for NCCL's all-to-all)
+    const int world = world_;
+    const int h = (int)((blockIdx.x % world + g + 1) % world);
+    const long long k0 = (long long)blockIdx.y * 64, c0 = (long long)(blockIdx.x / world) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long long c = c0 + tx;
     if (c < W) {
@@ -469,7 +472,8 @@ Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, l
     for (int i = 0; i < 16; i++) pp.p[i] = i < world ? peer_recv[i] : nullptr;
     const long long gx = (w + 31) / 32, gy = (K + 63) / 64;
     if (gy > 65535) return invalid("fourstep_exchange: grid too large");
-    fourstep_exchange_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)world), 256, 0, st>>>(slab, pp, K, w, rank, log2n);
+    // gridDim.z only carries the world size; the peer is picked from blockIdx.x
+    fourstep_exchange_kernel<<<dim3((unsigned)(gx * world), (unsigned)gy, 1), 256, 0, st>>>(slab, pp, K, w, rank, log2n, world);
     g_launches++;
     GD_CUDA(cudaGetLastError());
     return GD_OK;
@@ -478,15 +482,17 @@ Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, l
 // FFT2 on row blocks: both exchanges are strided block copies into peer memory (no repack kernels, no NCCL data
 // movement). For every peer h: dst_h[dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c], r < rows, c < cols.
 __global__ void __launch_bounds__(256) peer_block_copy_kernel(const cpx* __restrict__ src, PeerPtrs peers, long long rows, long long cols,
-                                                              long long src_step, long long src_pitch, long long dst_off, long long dst_pitch) {
-    const int h = blockIdx.z;
+                                                              long long src_step, long long src_pitch, long long dst_off, long long dst_pitch,
+                                                              int world, int rank) {
+    const int h = (int)((blockIdx.x % world + rank + 1) % world);      // consecutive blocks -> different peers, rotated by rank
+    const long long bx = blockIdx.x / world, nbx = gridDim.x / world;
     const cpx* s = src + (long long)h * src_step;
     cpx* d = peers.p[h] + dst_off;
     for (long long r = blockIdx.y; r < rows; r += gridDim.y)
-        for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += (long long)gridDim.x * blockDim.x)
+        for (long long c = bx * blockDim.x + threadIdx.x; c < cols; c += nbx * blockDim.x)
             d[r * dst_pitch + c] = s[r * src_pitch + c];
 }
-Status peer_block_copy(const cpx* src, cpx* const* peers, int world, long long rows, long long cols, long long src_step,
+Status peer_block_copy(const cpx* src, cpx* const* peers, int world, int rank, long long rows, long long cols, long long src_step,
                        long long src_pitch, long long dst_off, long long dst_pitch, cudaStream_t st) {
     if (!src || !peers || world < 1 || world > 16 || rows < 1 || cols < 1) return invalid("peer_block_copy: bad arguments");
     PeerPtrs pp;
@@ -494,7 +500,7 @@ Status peer_block_copy(const cpx* src, cpx* const* peers, int world, long long r
     long long gx = (cols + 255) / 256;
     if (gx > 64) gx = 64;
     long long gy = rows < 4096 ? rows : 4096;
-    peer_block_copy_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)world), 256, 0, st>>>(src, pp, rows, cols, src_step, src_pitch, dst_off, dst_pitch);
+    peer_block_copy_kernel<<<dim3((unsigned)(gx * world), (unsigned)gy, 1), 256, 0, st>>>(src, pp, rows, cols, src_step, src_pitch, dst_off, dst_pitch, world, rank);
     g_launches++;
     GD_CUDA(cudaGetLastError());
     return GD_OK;

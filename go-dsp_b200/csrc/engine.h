@@ -131,7 +131,7 @@ Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0
 Status repack_gkw(const cpx* in, cpx* out, long long G, long long K, long long W, cudaStream_t st);
 Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,
                          cudaStream_t st);
-Status peer_block_copy(const cpx* src, cpx* const* peers, int world, long long rows, long long cols, long long src_step,
+Status peer_block_copy(const cpx* src, cpx* const* peers, int world, int rank, long long rows, long long cols, long long src_step,
                        long long src_pitch, long long dst_off, long long dst_pitch, cudaStream_t st);
 Status transpose_batched(const cpx* in, cpx* out, long long batch, long long rows, long long cols, cudaStream_t st);
 // strided lines: `outer` blocks of `len` lines-elements with element stride s (fft_axis)

@@ -117,7 +117,7 @@ class PeerExchange:
 
     def block_copy(self, src, rows, cols, src_step, src_pitch, dst_off, dst_pitch):
         """every peer h: peer_buffer[h][dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c]"""
-        _capi.check(self.L.gd_peer_block_copy_dev(src.data_ptr(), self.ptr_array, self.world, rows, cols, src_step, src_pitch,
+        _capi.check(self.L.gd_peer_block_copy_dev(src.data_ptr(), self.ptr_array, self.world, self.rank, rows, cols, src_step, src_pitch,
                                                   dst_off, dst_pitch, self.ops._sp()))
 
     def close(self):

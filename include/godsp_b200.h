@@ -126,7 +126,7 @@ GD_API int gd_fourstep_exchange_dev(const double* slab_dev, void* const* peer_re
                                     int log2n, void* stream);
 /* FFT2 on row blocks: an exchange as strided block copies into peer memory; for every peer h (complex128 elements):
  * peers[h][dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c], r < rows, c < cols */
-GD_API int gd_peer_block_copy_dev(const double* src_dev, void* const* peers, int world, int64_t rows, int64_t cols, int64_t src_step,
+GD_API int gd_peer_block_copy_dev(const double* src_dev, void* const* peers, int world, int rank, int64_t rows, int64_t cols, int64_t src_step,
                                   int64_t src_pitch, int64_t dst_off, int64_t dst_pitch, void* stream);
 /* cudaMalloc'ed buffer + its 64-byte CUDA IPC handle; open / close a peer's handle in this process */
 GD_API int gd_ipc_alloc(void** p, size_t bytes, unsigned char* handle64);
