@@ -174,6 +174,7 @@ int64_t gd_bluestein_padded_len(int64_t n) {
 static int fft_host(const double* in, double* out, int64_t n, int64_t batch, bool real_in, int dir) {
     if (!in || !out || n < 1 || batch < 1 || (dir != 1 && dir != -1)) return (int)invalid_arg("fft: bad arguments");
     GD_ENTER();
+    ScratchOrder order__(d, d.stream);
     GD_TRY(ensure_events(d.dev));
     StageEvents& ev = g_ev[d.dev];
     const size_t in_el = real_in ? sizeof(double) : sizeof(cpx);
@@ -224,6 +225,7 @@ int gd_fft_batch_c2c(const double* in, double* out, int64_t n, int64_t batch, in
 int gd_convolve_c2c(const double* x, const double* y, double* out, int64_t n) {
     if (!x || !y || !out || n < 1) return (int)invalid_arg("convolve: bad arguments");
     GD_ENTER();
+    ScratchOrder order__(d, d.stream);
     cpx *din, *dout;
     GD_TRY(d.ensure_scratch(SCR_STAGE_IN, 2 * (size_t)n * sizeof(cpx), (void**)&din));
     GD_TRY(d.ensure_scratch(SCR_STAGE_OUT, (size_t)n * sizeof(cpx), (void**)&dout));
@@ -240,6 +242,7 @@ int gd_fftn_c2c(const double* in, double* out, const int64_t* dims, int nd, int 
     long long ld[16], total = 1;
     for (int i = 0; i < nd; i++) { if (dims[i] < 1) return (int)invalid_arg("fftn: invalid dimensions"); ld[i] = dims[i]; total *= dims[i]; }
     GD_ENTER();
+    ScratchOrder order__(d, d.stream);
     cpx* buf;
     GD_TRY(d.ensure_scratch(SCR_STAGE_OUT, (size_t)total * sizeof(cpx), (void**)&buf));
     GD_TRY(up(d, buf, in, (size_t)total * sizeof(cpx), d.stream));
@@ -277,6 +280,7 @@ int gd_pwelch_f64(const double* x, int64_t nx, int64_t nfft, int64_t noverlap, i
     const int64_t stride = nfft - noverlap;
     if ((nsegs - 1) * stride + nfft > nx) return (int)invalid_arg("pwelch: x shorter than nsegs segments");
     GD_ENTER();
+    ScratchOrder order__(d, d.stream);
     GD_TRY(ensure_events(d.dev));
     StageEvents& ev = g_ev[d.dev];
     // stream the signal through two device buffers, a range of whole segments at a time
@@ -359,16 +363,19 @@ int gd_fill_splitmix_dev(double* dst, int64_t n, uint64_t seed, uint64_t offset,
 int gd_fft_batch_c2c_dev(const double* in, double* out, int64_t n, int64_t batch, int dir, void* stream) {
     if (!in || !out || n < 1 || batch < 1 || (dir != 1 && dir != -1)) return (int)invalid_arg("fft_dev: bad arguments");
     GD_ENTER();
+    ScratchOrder order__(d, pick(d, stream));
     return (int)fft1d(d, in, n, (cpx*)out, n, n, batch, false, dir, pick(d, stream));
 }
 int gd_fft_batch_r2c_full_dev(const double* in, double* out, int64_t n, int64_t batch, int dir, void* stream) {
     if (!in || !out || n < 1 || batch < 1 || (dir != 1 && dir != -1)) return (int)invalid_arg("fft_dev: bad arguments");
     GD_ENTER();
+    ScratchOrder order__(d, pick(d, stream));
     return (int)fft1d(d, in, n, (cpx*)out, n, n, batch, true, dir, pick(d, stream));
 }
 int gd_convolve_c2c_dev(const double* x, const double* y, double* out, int64_t n, void* stream) {
     if (!x || !y || !out || n < 1) return (int)invalid_arg("convolve_dev: bad arguments");
     GD_ENTER();
+    ScratchOrder order__(d, pick(d, stream));
     return (int)convolve(d, (const cpx*)x, (const cpx*)y, (cpx*)out, n, pick(d, stream));
 }
 int gd_fftn_c2c_dev(const double* in, double* out, const int64_t* dims, int nd, int dir, void* stream) {
@@ -376,6 +383,7 @@ int gd_fftn_c2c_dev(const double* in, double* out, const int64_t* dims, int nd, 
     long long ld[16];
     for (int i = 0; i < nd; i++) ld[i] = dims[i];
     GD_ENTER();
+    ScratchOrder order__(d, pick(d, stream));
     return (int)fftn(d, (const cpx*)in, (cpx*)out, ld, nd, dir, pick(d, stream));
 }
 int gd_fourstep_twiddle_dev(double* blk, int64_t rows, int64_t cols, int64_t row0, int64_t col0, int log2n, void* stream) {
@@ -434,12 +442,14 @@ int gd_transpose_batched_dev(const double* in, double* out, int64_t batch, int64
 int gd_fft_strided_c2c_dev(const double* in, double* out, int64_t outer, int64_t len, int64_t stride, int dir, void* stream) {
     if (!in || !out || (dir != 1 && dir != -1)) return (int)invalid_arg("fft_strided_dev: bad arguments");
     GD_ENTER();
+    ScratchOrder order__(d, pick(d, stream));
     return (int)fft_strided(d, (const cpx*)in, (cpx*)out, outer, len, stride, dir, pick(d, stream));
 }
 int gd_pwelch_partial_dev(const double* x, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp, int64_t seg0,
                           int64_t nseg, const double* win, double* raw, void* stream) {
     if (!x || !win || !raw || noverlap < 0 || noverlap >= nfft) return (int)invalid_arg("pwelch_dev: bad arguments");
     GD_ENTER();
+    ScratchOrder order__(d, pick(d, stream));
     return (int)pwelch_partial(d, x, nfft, nfft - noverlap, fftlen, lp, seg0, nseg, win, raw, pick(d, stream));
 }
 int gd_pwelch_finalize_dev(const double* raw, int64_t lp, int64_t nsegs, double norm, double* pxx, void* stream) {

@@ -102,6 +102,7 @@ void Device::destroy() {
     if (!ready) return;
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
+    if (scratch_evt) { cudaEventDestroy(scratch_evt); scratch_evt = nullptr; scratch_used = false; }
     for (auto& w : wl) { if (w) cudaFree(w); w = nullptr; }
     for (auto& kv : tw) { cudaFree(kv.second.lo); if (kv.second.hi) cudaFree(kv.second.hi); }
     tw.clear();

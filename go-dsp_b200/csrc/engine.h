@@ -94,6 +94,11 @@ struct Device {
     bool tma_p1_bulk = true;             // pass-1 output through the async proxy (staged bulk stores, published on completion)
     int tma_dbg = 0;                     // bisecting switches of the fused kernel (bit 0: acquire load instead of fence, bit 1: unsplit drain, bit 2: no fence by the storing warps, bit 3: writer-side proxy fence)
     int tma_delay = 1;                   // phases between P1(g) and P2(g); delay + 2 slots of 16 MiB must stay in L2
+    // The scratch blocks, dependency counters and the persisting L2 window are per device, not per stream: a call on
+    // another stream first waits (on the device) for the previous user, see ScratchOrder.
+    cudaEvent_t scratch_evt = nullptr;
+    cudaStream_t scratch_last = nullptr;
+    bool scratch_used = false;
     std::recursive_mutex mu;             // every public entry point locks its device
 
     Status init(int device);
@@ -103,6 +108,20 @@ struct Device {
     Status l2_release();
     Status twiddles(int log2m, TwiddleTable* out);
     Status bluestein(long long n, cudaStream_t st, const BluesteinPlan** out);
+};
+
+// Stream-orders the users of the device's shared scratch state: construct after locking the device, before any work is
+// enqueued on `st`; the destructor records the hand-over point.
+struct ScratchOrder {
+    Device& d;
+    cudaStream_t st;
+    ScratchOrder(Device& dev, cudaStream_t s) : d(dev), st(s) {
+        if (d.scratch_used && d.scratch_last != st && d.scratch_evt) cudaStreamWaitEvent(st, d.scratch_evt, 0);
+    }
+    ~ScratchOrder() {
+        if (!d.scratch_evt) cudaEventCreateWithFlags(&d.scratch_evt, cudaEventDisableTiming);
+        if (d.scratch_evt) { cudaEventRecord(d.scratch_evt, st); d.scratch_last = st; d.scratch_used = true; }
+    }
 };
 
 // ---- transforms (device pointers) ----------------------------------------------------------

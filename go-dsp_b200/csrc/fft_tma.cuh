@@ -782,32 +782,32 @@ fft_tma_fused2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                         } else tfc = w.tf;
                     }
                 } else {
-                item = tokens ? nitems : atomicAdd(a.queue, 1);
-                token = item >= nitems;
-                if (!token) {
-                    w = tma_decode(item, B, D);
-                    if (w.type == 0) {
-                        if (w.tf >= S && !(a.dbg_nodeps & 2)) { while (ld_relaxed_gpu(a.done2 + (w.tf - S)) < TPT) __nanosleep(32); }
-                        tfc = w.tf;
-                    } else {
-                        if (w.tf != ready_tf) {             // one poll + fence pair per transform, not per tile
-                            if (!(a.dbg_nodeps & 1)) { while (ld_relaxed_gpu(a.done1 + w.tf) < TPT) __nanosleep(32); }
-                            // Acquire with a full fence. An acquire load + fence.proxy.async.global is about 2.5 % faster (the
-                            // MEMBAR also waits for this lane's own tile loads in flight, ~2000 cycles on the phase boundary), but
-                            // the stress test still showed a stale tile about once per 1500 runs of 256 transforms at delay 2 with
-                            // it (0 of 2000 with the fences), so the fences stay; `dbg_acqload` keeps the variant measurable.
-                            if (a.dbg_acqload) {
-                                (void)ld_acquire_gpu(a.done1 + w.tf);
-                                asm volatile("fence.proxy.async.global;\n" ::: "memory");
-                            } else {
-                                asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
-                                asm volatile("fence.proxy.async;\n" ::: "memory");   // other CTAs' generic-proxy stores -> this async-proxy read
+                    item = tokens ? nitems : atomicAdd(a.queue, 1);
+                    token = item >= nitems;
+                    if (!token) {
+                        w = tma_decode(item, B, D);
+                        if (w.type == 0) {
+                            if (w.tf >= S && !(a.dbg_nodeps & 2)) { while (ld_relaxed_gpu(a.done2 + (w.tf - S)) < TPT) __nanosleep(32); }
+                            tfc = w.tf;
+                        } else {
+                            if (w.tf != ready_tf) {             // one poll + fence pair per transform, not per tile
+                                if (!(a.dbg_nodeps & 1)) { while (ld_relaxed_gpu(a.done1 + w.tf) < TPT) __nanosleep(32); }
+                                // Acquire with a full fence. An acquire load + fence.proxy.async.global is about 2.5 % faster (the
+                                // MEMBAR also waits for this lane's own tile loads in flight, ~2000 cycles on the phase boundary), but
+                                // the stress test still showed a stale tile about once per 1500 runs of 256 transforms at delay 2 with
+                                // it (0 of 2000 with the fences), so the fences stay; `dbg_acqload` keeps the variant measurable.
+                                if (a.dbg_acqload) {
+                                    (void)ld_acquire_gpu(a.done1 + w.tf);
+                                    asm volatile("fence.proxy.async.global;\n" ::: "memory");
+                                } else {
+                                    asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+                                    asm volatile("fence.proxy.async;\n" ::: "memory");   // other CTAs' generic-proxy stores -> this async-proxy read
+                                }
+                                ready_tf = w.tf;
                             }
-                            ready_tf = w.tf;
+                            tm = &tm_int; tfc = w.tf % S;
                         }
-                        tm = &tm_int; tfc = w.tf % S;
                     }
-                }
                 }
                 log[it & 31] = token ? -1 : item;
                 __threadfence_block();

@@ -359,3 +359,27 @@ def test_edge_cases(gd):
     godsp.fft.FFT(x)
     assert np.array_equal(x, keep)                                # inputs are never modified
     assert gd[2].gd_kernel_launches() > 0
+
+
+def test_two_streams_share_the_device_scratch(gd):
+    """Calls on different streams use the same scratch slots and dependency counters: the library orders them on the
+    device, so back-to-back batches on two streams must both come out right."""
+    _, capi, L = gd
+    import torch
+    n, b = 1 << 20, 24
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    x1 = torch.empty(b * n * 2, dtype=torch.float64, device="cuda")
+    x2 = torch.empty_like(x1)
+    capi.check(L.gd_fill_splitmix_dev(x1.data_ptr(), b * n * 2, 21, 0, None))
+    capi.check(L.gd_fill_splitmix_dev(x2.data_ptr(), b * n * 2, 22, 0, None))
+    capi.check(L.gd_stream_sync(None))
+    y1, y2 = torch.empty_like(x1), torch.empty_like(x2)
+    for _ in range(5):
+        capi.check(L.gd_fft_batch_c2c_dev(x1.data_ptr(), y1.data_ptr(), n, b, 1, C.c_void_p(s1.cuda_stream)))
+        capi.check(L.gd_fft_batch_c2c_dev(x2.data_ptr(), y2.data_ptr(), n, b, 1, C.c_void_p(s2.cuda_stream)))
+    torch.cuda.synchronize()
+    for x, y in ((x1, y1), (x2, y2)):
+        ex, ey = (x.view(b, -1) ** 2).sum(1), (y.view(b, -1) ** 2).sum(1)
+        assert float(((ey / n - ex).abs() / ex).max()) < 1e-13
+        row = x.view(b, -1)[b - 1].cpu().numpy().view(np.complex128)
+        assert rel_l2(y.view(b, -1)[b - 1].cpu().numpy().view(np.complex128), oracle.fft(row)) <= TOL
