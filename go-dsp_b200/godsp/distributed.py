@@ -126,6 +126,7 @@ class PeerExchange:
         for p in self.opened:
             _capi.check(self.L.gd_ipc_close(p))
         self.opened = []
+        dist.barrier(group=self.group)              # nobody has this rank's buffer mapped any more
         del self.recv
         _capi.check(self.L.gd_dev_free(self.own))
 

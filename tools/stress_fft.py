@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Race hunt for the fused 2^20 kernel: repeat a batched transform and check Parseval on every row (a wrong tile
 changes a row's energy by O(1)). usage: stress_fft.py [--batch 256] [--reps 20] "opt=val,..." ..."""
-import ctypes as C, os, sys
+import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "go-dsp_b200"))
