@@ -121,6 +121,75 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+
+# --------------------------------------------------------------------------- parity (outside every timed region)
+PARITY_TOL = 1e-12            # BASELINE.json north_star: relative L2 <= 1e-12 for spectra and PSDs
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+    d = float(np.linalg.norm(b))
+    return float(np.linalg.norm(a - b)) / d if d else float(np.linalg.norm(a - b))
+
+
+def allmax(torch, dist, world, v):
+    if world > 1:
+        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return float(v)
+
+
+def dft_phasors(torch, length, k, sign=-1.0):
+    """exp(sign * 2 pi i * (i*k mod length) / length), i < length, exponent reduced exactly in int64"""
+    i = torch.arange(length, dtype=torch.int64, device="cuda")
+    ang = (sign * 2.0 * np.pi / length) * ((i * int(k)) % length).double()
+    return torch.complex(torch.cos(ang), torch.sin(ang))
+
+
+def parity_fft_rows(torch, y, n, row0, rows):
+    """sampled rows of the timed batch against oracle.fft of the same SplitMix64 rows (fft/fft.go:72-87)"""
+    import oracle
+    worst, per = 0.0, {}
+    for r in rows:
+        got = y[2 * n * r: 2 * n * (r + 1)].cpu().numpy().view(np.complex128)
+        x = oracle.splitmix_complex(n, FFT_SEED, (row0 << 21) + (r << 20))
+        e = rel_l2(got, oracle.fft(x))
+        per[str(r)] = e
+        worst = max(worst, e)
+    return worst, per
+
+
+def parity_fft2(torch, dist, world, rank, src_blk, out_blk, R, Cc, rows, cols):
+    """fft.FFT2 output (row blocks `out_blk` of the R x Cc result) on sampled rows and columns. One output line is the
+    oracle's 1-D transform (CPU) of one bin of the other axis, and that bin is a plain float64 matrix-vector product
+    with exactly reduced phasors (torch, not this library): out[r, :] = FFT(f_r^T . src), out[:, c] = FFT(src . f_c)."""
+    import oracle
+    rg = R // world
+    s2, o2 = src_blk.view(rg, Cc), out_blk.view(rg, Cc)
+    worst = 0.0
+    for r in rows:
+        f = dft_phasors(torch, R, r)[rank * rg:(rank + 1) * rg]
+        u = torch.mv(s2.t(), f)                                   # partial sum over this rank's rows
+        if world > 1:
+            dist.all_reduce(u)
+        if r // rg == rank:
+            e = rel_l2(o2[r - rank * rg].cpu().numpy(), oracle.fft(u.cpu().numpy()))
+            worst = max(worst, e)
+    for c in cols:
+        v = torch.mv(s2, dft_phasors(torch, Cc, c))               # this rank's rows of the bin-c vector
+        got = o2[:, c].contiguous()
+        if world > 1:
+            vs = [torch.empty_like(v) for _ in range(world)]
+            gs = [torch.empty_like(got) for _ in range(world)]
+            dist.all_gather(vs, v)
+            dist.all_gather(gs, got)
+            v, got = torch.cat(vs), torch.cat(gs)
+        if rank == 0:
+            worst = max(worst, rel_l2(got.cpu().numpy(), oracle.fft(v.cpu().numpy())))
+    return allmax(torch, dist, world, worst)
+
+
 def dist_setup(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -292,6 +361,12 @@ def run_ours(args):
         capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, batch, 1, sp))
 
     ms, launches, clocks = timed(fft_step, args.steps, args.warmup)
+    parity = {}
+    # sampled rows of the timed batch vs the oracle: first / last row of the first / last 128-transform launch
+    prow = sorted(set(r for r in (0, min(127, batch - 1), max(0, batch - 128), batch - 1)))
+    w_fft, per_row = parity_fft_rows(torch, y, n, row0, prow)
+    parity["fft_batch"] = {"max_rel_l2": allmax(torch, dist, world, w_fft), "rows_per_rank": prow,
+                           "vs": "oracle.fft (C restatement of fft/radix2.go) on the same SplitMix64 rows, every rank"}
     pts = batch * n * world
     value = pts / (ms * 1e-3) / 1e9
     per_gpu_bytes = 32.0 * batch * n
@@ -367,10 +442,19 @@ def run_ours(args):
             if px is not None:
                 px.close()
 
+    for key in ("pwelch", "fft2", "fft_1d_sharded"):
+        if key in line and "_parity" in line[key]:
+            parity[key] = line[key].pop("_parity")
+    parity["max_rel_l2"] = max([v["max_rel_l2"] for v in parity.values()] or [0.0])
+    parity["tolerance"] = PARITY_TOL
+    parity["ok"] = bool(parity["max_rel_l2"] <= PARITY_TOL)
+    line["parity"] = parity
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not parity["ok"]:
+        raise SystemExit("bench.py: parity check failed: %r" % (parity,))
 
 
 def run_fft2(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
@@ -405,15 +489,75 @@ def run_fft2(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
             D.fft2_sharded(src, R, Cc, ops, peers=peers, out=res)
         api = "godsp.distributed.fft2_sharded(peers=...): block copy into the peers' column slabs over NVLink, column lines, block copy back into the peers' row blocks, row lines (gd_peer_block_copy_dev; no NCCL data movement)"
     ms, launches, clocks = timed(step, steps, warmup)
+    result = out if world == 1 else res
+    w2 = parity_fft2(torch, dist, world, rank, src, result, R, Cc, rows=(0, 1, 5461, R - 1), cols=(0, 3, 8192, Cc - 1))
+    par = {"max_rel_l2": w2, "vs": "sampled output rows and columns of the timed 16384 x 16384 result vs oracle.fft of the matching "
+                                   "single-bin DFT of the other axis (float64 matrix-vector product with exactly reduced phasors)"}
     if peers is not None:
         peers[0].close()
         peers[1].close()
-    return {"metric": "FFT2 Gelem/s (complex128, 16384 x 16384)", "value": R * Cc / (ms * 1e-3) / 1e9, "unit": "Gelem/s",
+    return {"_parity": par, "metric": "FFT2 Gelem/s (complex128, 16384 x 16384)", "value": R * Cc / (ms * 1e-3) / 1e9, "unit": "Gelem/s",
             "ms_per_step": ms, "scaling": "strong", "api": api, **extra,
             "roofline": {"bound": "hbm", "achieved": 64.0 * R * Cc / world / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": 64.0 * R * Cc / world / (ms * 1e-3) / 1e9 / hbm_peak,
                          "note": "64 B per element algorithmic: two sweeps, the 4 GiB matrix is far larger than L2 (SURVEY.md 8d)"},
             "clocks": clocks, "_launches": int(launches)}
+
+
+def sharded_1d_kat(torch, dist, D, ops, px, n, world, rank, src, work):
+    """Known-answer test at the full size: x[n] = delta[n - p] + sum_t a exp(2 pi i f_t n / N) (integer bins f_t), so
+    X[k] = exp(-2 pi i p k / N) + N a [k == f_t]. Built and checked on the device in exact integer phase arithmetic."""
+    n1, n2, k, w = D.split_1d(n, world)
+    mask, p, amp = n - 1, 1234567891 % n, 2.0 ** -16
+    tones = [f % n for f in (3, 987654321, n // 2 + 12345)]
+    s2 = src.view(n1, w)
+    rows = max(1, (1 << 24) // w)
+    for a in range(0, n1, rows):
+        r = torch.arange(a, min(n1, a + rows), dtype=torch.int64, device="cuda")[:, None]
+        idx = r * n2 + (rank * w + torch.arange(w, dtype=torch.int64, device="cuda"))[None, :]
+        acc = (idx == p).to(torch.complex128)
+        for f in tones:
+            ang = (2.0 * np.pi / n) * ((idx * f) & mask).double()
+            acc += amp * torch.complex(torch.cos(ang), torch.sin(ang))
+        s2[a:a + rows] = acc
+    D.fft_1d_sharded(src, n, ops, work=work, peer=px)
+    torch.cuda.synchronize()
+    o2 = work.view(n2, k)
+    num = torch.zeros((), dtype=torch.float64, device="cuda")
+    den = torch.zeros((), dtype=torch.float64, device="cuda")
+    rows = max(1, (1 << 24) // k)
+    for a in range(0, n2, rows):
+        k2 = torch.arange(a, min(n2, a + rows), dtype=torch.int64, device="cuda")[:, None]
+        kk = (rank * k + torch.arange(k, dtype=torch.int64, device="cuda"))[None, :] + n1 * k2
+        ang = (-2.0 * np.pi / n) * ((kk * p) & mask).double()
+        want = torch.complex(torch.cos(ang), torch.sin(ang))
+        for f in tones:
+            want += (kk == f).to(torch.complex128) * (amp * n)
+        d = o2[a:a + rows] - want
+        num += (d.real ** 2 + d.imag ** 2).sum()
+        den += (want.real ** 2 + want.imag ** 2).sum()
+    t = torch.stack([num, den])
+    dist.all_reduce(t)
+    return float(torch.sqrt(t[0] / t[1]).item())
+
+
+def sharded_1d_vs_oracle(torch, dist, D, ops, world, rank, lg=24):
+    """the same peer-memory code path at 2^lg points against oracle.fft (rank 0 compares the gathered spectrum)"""
+    import oracle
+    n = 1 << lg
+    n1, n2, k, w = D.split_1d(n, world)
+    x = oracle.splitmix_complex(n, 6)
+    slab = D.scatter_signal(torch.from_numpy(x), n, rank, world).cuda()
+    px = D.PeerExchange(n1 * w, ops)
+    out = D.fft_1d_sharded(slab, n, ops, peer=px)
+    torch.cuda.synchronize()
+    slabs = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(slabs, out)
+    err = 0.0
+    if rank == 0:
+        err = rel_l2(D.gather_spectrum(slabs, n).cpu().numpy(), oracle.fft(x))
+    px.close()
+    return allmax(torch, dist, world, err)
 
 
 def run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed):
@@ -440,18 +584,23 @@ def run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed):
     px = D.PeerExchange(n1 * w, ops)
 
     def step():
-        slab.copy_(src)
-        D.fft_1d_sharded(slab, n, ops, work=work, peer=px)
+        D.fft_1d_sharded(src, n, ops, work=work, peer=px)       # the peer-memory path leaves its input untouched
     ms, launches, clocks = timed(step, steps, warmup)
     # Parseval on the last step: sum |X|^2 = n * sum |x|^2 over all ranks
     e = torch.stack([(work.real ** 2 + work.imag ** 2).sum(), (src.real ** 2 + src.imag ** 2).sum()])
     dist.all_reduce(e)
-    return {"metric": "single 1-D FFT GS/s (complex128, 2^%d points over %d GPUs)" % (lg, world), "value": n / (ms * 1e-3) / 1e9,
+    parseval = abs(float(e[0].item()) / (n * float(e[1].item())) - 1.0)
+    kat = sharded_1d_kat(torch, dist, D, ops, px, n, world, rank, src, work)
+    small = sharded_1d_vs_oracle(torch, dist, D, ops, world, rank, 24)
+    par = {"max_rel_l2": max(kat, small), "kat_full_size_rel_l2": kat, "oracle_2p24_rel_l2": small, "parseval_rel_err": parseval,
+           "vs": "impulse + three integer-bin tones at the full 2^%d points (closed form, exact integer phases); the same "
+                 "peer-memory path at 2^24 points vs oracle.fft" % lg}
+    return {"_parity": par, "metric": "single 1-D FFT GS/s (complex128, 2^%d points over %d GPUs)" % (lg, world), "value": n / (ms * 1e-3) / 1e9,
             "unit": "GS/s", "ms_per_step": ms, "scaling": "weak", "log2n": lg,
-            "api": "godsp.distributed.fft_1d_sharded(peer=PeerExchange): strided lines, ONE kernel for twiddle + transpose + NVLink P2P stores into the peers' buffers (gd_fourstep_exchange_dev), strided lines (+ one device copy of the slab per step)",
+            "api": "godsp.distributed.fft_1d_sharded(peer=PeerExchange): strided lines, ONE kernel for twiddle + transpose + NVLink P2P stores into the peers' buffers (gd_fourstep_exchange_dev), strided lines",
             "nccl_all_to_all_variant_ms": ms_nccl,
             "all_to_all_bytes_per_gpu": 16 * (n // world) * (world - 1) // world,
-            "parseval_rel_err": abs(float(e[0].item()) / (n * float(e[1].item())) - 1.0),
+            "parseval_rel_err": parseval,
             "clocks": clocks, "_launches": int(launches), "_peer": px}
 
 
@@ -491,6 +640,32 @@ def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_
             capi.check(L.gd_pwelch_finalize_dev(raw.data_ptr(), lp, nsegs, norm, pxx.data_ptr(), sp))
 
     ms, launches, clocks = timed(step, args.steps, args.warmup)
+    # ---- parity, outside the timed region
+    # (1) the full-size result against a size-independent property (Parseval over every windowed segment):
+    #     sum_j pxx[j] = L * sum_segs sum_n (w[n] x[n])^2 / (nsegs * norm)          (spectral/pwelch.go:113-121,134-136)
+    tsum = torch.zeros((), dtype=torch.float64, device="cuda")
+    segs = x.unfold(0, nfft, stride)                       # view, no copy: [local segments][nfft]
+    for a in range(0, s1 - s0, 8192):
+        blk = segs[a:min(a + 8192, s1 - s0)] * dwin
+        tsum += (blk * blk).sum()
+    if world > 1:
+        dist.all_reduce(tsum)
+    want_sum = nfft * float(tsum.item()) / (nsegs * norm)
+    parseval = abs(float(pxx.sum().item()) / want_sum - 1.0)
+    # (2) the same kernel on a 2^24-sample prefix of this rank's signal against oracle.pwelch
+    import oracle
+    npre = min(1 << 24, ns_local)
+    xo = oracle.fill_splitmix(npre, PW_SEED, rank * ns_local)
+    want, _ = oracle.pwelch(xo, 1.0, nfft=nfft, noverlap=nov, threads=min(8, os.cpu_count() or 1))
+    nsegs_pre = (npre - nfft) // stride + 1
+    raw2 = torch.empty(lp, dtype=torch.float64, device="cuda")
+    pxx2 = torch.empty(lp, dtype=torch.float64, device="cuda")
+    capi.check(L.gd_pwelch_partial_dev(x.data_ptr(), nfft, nov, nfft, lp, 0, nsegs_pre, dwin.data_ptr(), raw2.data_ptr(), sp))
+    capi.check(L.gd_pwelch_finalize_dev(raw2.data_ptr(), lp, nsegs_pre, norm, pxx2.data_ptr(), sp))
+    torch.cuda.synchronize()
+    e_pre = rel_l2(pxx2.cpu().numpy(), want)
+    par = {"max_rel_l2": allmax(torch, dist, world, max(e_pre, parseval)), "prefix_rel_l2": e_pre, "parseval_rel_err_full_size": parseval,
+           "vs": "oracle.pwelch on a 2^%d-sample prefix of every rank's signal; Parseval over all %d windowed segments of the timed run" % (npre.bit_length() - 1, nsegs)}
     value = total / (ms * 1e-3) / 1e6
     achieved = 8.0 * ns_local / (ms * 1e-3) / 1e9
     out = {
@@ -501,7 +676,7 @@ def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_
         "roofline": {"bound": "hbm", "kernel": "gd::pwelch_fused_kernel<12>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": ncu_traffic("pwelch_fused_kernel"),
                      "note": "8 B per input sample (SURVEY.md 8d); FP64 issue rate, not HBM, is the tighter roof for this kernel (DESIGN.md)"},
-        "clocks": clocks, "_launches": int(launches),
+        "clocks": clocks, "_launches": int(launches), "_parity": par,
         "pxx_checksum": float(pxx.sum().item()),
     }
     if "e2e" not in skip:

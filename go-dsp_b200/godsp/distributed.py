@@ -147,7 +147,8 @@ def split_1d(n, world):
 
 
 def fft_1d_sharded(slab, n, ops, group=None, work=None, peer=None):
-    """Forward transform of one n-point signal.  `slab`: this rank's [N1][W] column slab (flattened, overwritten).
+    """Forward transform of one n-point signal.  `slab`: this rank's [N1][W] column slab (flattened; overwritten by the
+    NCCL formulation, preserved by the peer-memory one).
     Returns this rank's [N2][K] slab of the spectrum (a new tensor, or `work` if given: n/world elements).
     peer: a PeerExchange of n/world elements -> the exchange step is ONE kernel storing into the peers' buffers over
     NVLink (twiddle + transpose fused in); otherwise twiddle kernel + NCCL all-to-all + transpose kernel."""
@@ -157,9 +158,9 @@ def fft_1d_sharded(slab, n, ops, group=None, work=None, peer=None):
         raise ValueError("slab has %d elements, expected %d" % (slab.numel(), n1 * w))
     if peer is not None:
         out = work if work is not None else ops.empty(n1 * w)
-        ops.fft_strided(slab, slab, 1, n1, w, 1)          # lines over n1
+        ops.fft_strided(slab, out, 1, n1, w, 1)           # lines over n1, into `out` (the slab is left untouched)
         peer.fence()                                      # every rank is done reading its receive buffer (previous call)
-        peer.exchange(slab, n1, w, _ilog2(n))             # peer h gets [rank*W + c][k] <- slab[h*K + k][c] * w_N^(k1 n2)
+        peer.exchange(out, n1, w, _ilog2(n))              # peer h gets [rank*W + c][k] <- out[h*K + k][c] * w_N^(k1 n2)
         peer.fence()                                      # every rank's stores have landed
         ops.fft_strided(peer.recv, out, 1, n2, k, 1)      # lines over n2
         return out
