@@ -143,15 +143,17 @@ int gd_use_device(int dev) {
 int gd_set_option(const char* key, int64_t value) {
     GD_ENTER();
     if (!strcmp(key, "pass_scratch_mb")) { if (value < 1) return (int)invalid_arg("pass_scratch_mb < 1"); d.pass_scratch_budget = (size_t)value << 20; }
+    else if (!strcmp(key, "l2_block_mb")) { if (value < 1) return (int)invalid_arg("l2_block_mb < 1"); d.l2_block_budget = (size_t)value << 20; }
+    else if (!strcmp(key, "two_stream_chunks")) d.two_stream_chunks = value != 0;
     else if (!strcmp(key, "wide_tiles")) d.wide_tiles = value != 0;
     else if (!strcmp(key, "fused")) d.use_fused = value != 0;
     else if (!strcmp(key, "debug_alias")) d.debug_alias = value != 0;
     else if (!strcmp(key, "w32")) { if (value < 0 || value > 6) return (int)invalid_arg("w32 out of range"); d.w32 = (int)value; }
     else if (!strcmp(key, "tma")) d.use_tma = value != 0;
-    else if (!strcmp(key, "tma_two_queues")) { if (value < 0 || value > 4) return (int)invalid_arg("tma_two_queues out of range"); d.tma_two_queues = (int)value; }
-    else if (!strcmp(key, "tma_dbg")) d.tma_dbg = (int)value;
-    else if (!strcmp(key, "tma_p1_bulk")) d.tma_p1_bulk = value != 0;
+    else if (!strcmp(key, "tma_opt")) d.tma_opt = (int)value;
+    else if (!strcmp(key, "tma_prof")) d.tma_prof = value != 0;
     else if (!strcmp(key, "tma_delay")) { if (value < 0 || value > 4) return (int)invalid_arg("tma_delay out of range"); d.tma_delay = (int)value; }
+    else if (!strcmp(key, "tma_slots")) { if (value < 2 || value > 6) return (int)invalid_arg("tma_slots out of range"); d.tma_slots = (int)value; }
     else if (!strcmp(key, "tiled_scratch")) d.tiled_scratch = value != 0;
     else if (!strcmp(key, "l2_window")) d.use_l2_window = value != 0;
     else if (!strcmp(key, "fused_delay")) { if (value < 1 || value > 6) return (int)invalid_arg("fused_delay out of range"); d.fused_delay = (int)value; }
@@ -161,6 +163,16 @@ int gd_set_option(const char* key, int64_t value) {
 }
 
 int64_t gd_kernel_launches(void) { return g_launches.load(); }
+
+int gd_tma_profile_read(int64_t* out, int max_ctas) {
+    if (!out || max_ctas < 1) return (int)invalid_arg("gd_tma_profile_read: bad arguments");
+    GD_ENTER();
+    if (!d.scratch[SCR_PROF]) return (int)invalid_arg("gd_tma_profile_read: no profiled launch yet (gd_set_option(\"tma_prof\", 1))");
+    const int n = d.num_sms < max_ctas ? d.num_sms : max_ctas;
+    GD_CUDA(cudaDeviceSynchronize());
+    GD_CUDA(cudaMemcpy(out, d.scratch[SCR_PROF], (size_t)n * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return n;
+}
 
 int64_t gd_bluestein_padded_len(int64_t n) {
     int64_t need = 2 * n - 1, la = 1;

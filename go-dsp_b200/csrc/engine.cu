@@ -14,7 +14,7 @@ namespace gd {
 cudaError_t launch_fused(int log2l, bool wide, const FusedParams& a, long long total_items, int num_sms, cudaStream_t st);
 int fused_tile_lines(int log2l, bool wide);
 cudaError_t launch_pass32(int variant, const PassParams& a, int num_sms, cudaStream_t st);
-bool tma_fused_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist);
+bool tma_fused_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, int ld_conj, int st_conj, double scale);
 Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long batch, int ld_conj,
                     int st_conj, double scale, cudaStream_t st);
 int pass32_tile_lines(int variant);
@@ -76,6 +76,9 @@ Status Device::init(int device) {
     GD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     GD_CUDA(cudaStreamCreateWithFlags(&stream_in, cudaStreamNonBlocking));
     GD_CUDA(cudaStreamCreateWithFlags(&stream_out, cudaStreamNonBlocking));
+    GD_CUDA(cudaStreamCreateWithFlags(&stream_aux, cudaStreamNonBlocking));
+    GD_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    GD_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     for (int k = 5; k <= 12; k++) {
         std::vector<cpx> h;
         host_twiddles(h, 1LL << k, 1, 1LL << k);
@@ -85,6 +88,7 @@ Status Device::init(int device) {
         long v = atol(s);
         if (v > 0) pass_scratch_budget = (size_t)v << 20;
     }
+    if (const char* s = getenv("GD_L2_BLOCK_MB")) { long v = atol(s); if (v > 0) l2_block_budget = (size_t)v << 20; }
     if (const char* s = getenv("GD_WIDE_TILES")) wide_tiles = atoi(s) != 0;
     if (const char* s = getenv("GD_FUSED")) use_fused = atoi(s) != 0;
     if (const char* s = getenv("GD_TILED")) tiled_scratch = atoi(s) != 0;
@@ -109,8 +113,10 @@ void Device::destroy() {
     for (auto& kv : blue) { cudaFree(kv.second.chirp_inv); cudaFree(kv.second.bhat); }
     blue.clear();
     for (int i = 0; i < SCR_NSLOTS; i++) { if (scratch[i]) cudaFree(scratch[i]); scratch[i] = nullptr; scratch_bytes[i] = 0; }
-    cudaStreamDestroy(stream); cudaStreamDestroy(stream_in); cudaStreamDestroy(stream_out);
-    stream = stream_in = stream_out = nullptr;
+    cudaStreamDestroy(stream); cudaStreamDestroy(stream_in); cudaStreamDestroy(stream_out); cudaStreamDestroy(stream_aux);
+    cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
+    stream = stream_in = stream_out = stream_aux = nullptr;
+    ev_fork = ev_join = nullptr;
     ready = false;
 }
 
@@ -183,6 +189,20 @@ static PassParams base_params(Device& d, int log2l) {
     return p;
 }
 
+// Alternate independent chunks of one call between the caller's stream and the device's auxiliary stream.
+struct ForkJoin {
+    Device& d;
+    cudaStream_t st;
+    bool on;
+    ForkJoin(Device& dev, cudaStream_t s, bool enable) : d(dev), st(s), on(enable && dev.stream_aux && s != dev.stream_aux) {
+        if (on) { cudaEventRecord(d.ev_fork, st); cudaStreamWaitEvent(d.stream_aux, d.ev_fork, 0); }
+    }
+    cudaStream_t stream(long long i) const { return on && (i & 1) ? d.stream_aux : st; }
+    ~ForkJoin() {
+        if (on) { cudaEventRecord(d.ev_join, d.stream_aux); cudaStreamWaitEvent(st, d.ev_join, 0); }
+    }
+};
+
 // ------------------------------------------------------------------ power-of-two transforms
 Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, int log2n,
                 long long batch, const FusedOps& ops, cudaStream_t st) {
@@ -202,9 +222,12 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
     }
     if (log2n > 24) return invalid("fft_pow2: N > 2^24 needs the multi-GPU path");
     const bool lean = !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
-    if (d.use_tma && lean && log2n == 20 && !d.debug_alias && tma_fused_applicable(in, in_dist, out, out_dist))
-        return fft_tma_2p20(d, (const cpx*)in, in_dist, out, out_dist, batch, (ops.ld_flags & LD_CONJ) ? 1 : 0,
-                            (ops.st_flags & ST_CONJ) ? 1 : 0, (ops.st_flags & ST_SCALE) ? ops.scale : 1.0, st);
+    if (d.use_tma && lean && log2n == 20 && !d.debug_alias) {
+        const int lc = (ops.ld_flags & LD_CONJ) ? 1 : 0, sc = (ops.st_flags & ST_CONJ) ? 1 : 0;
+        const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
+        if (tma_fused_applicable(in, in_dist, out, out_dist, lc, sc, scl))
+            return fft_tma_2p20(d, (const cpx*)in, in_dist, out, out_dist, batch, lc, sc, scl, st);
+    }
     if (d.use_fused && lean && (log2n % 2) == 0 && log2n >= 16 && batch * (2LL << (log2n / 2)) < (1LL << 30)) {
         // both passes in one persistent kernel, intermediate resident in L2 (fft_fused.cuh)
         const int l = log2n / 2, T = fused_tile_lines(l, d.wide_tiles), tpt = (1 << l) / T;
@@ -267,14 +290,23 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
     const long long N1 = 1LL << l1, N2 = 1LL << l2;
     TwiddleTable tw;
     GD_TRY(d.twiddles(log2n, &tw));
-    long long chunk = (long long)(d.pass_scratch_budget / ((size_t)N * sizeof(cpx)));
+    // The inter-pass block of a chunk is written by pass 1 and read back by pass 2 right away: chunks are sized to stay
+    // in L2 (l2_block_budget), so HBM sees 32 B per point, not 64. Chunks alternate between two streams (two scratch
+    // blocks), which hides the launch gaps and tails of these short launches behind the other chunk's kernels.
+    const size_t budget = d.pass_scratch_budget < d.l2_block_budget ? d.pass_scratch_budget : d.l2_block_budget;
+    long long chunk = (long long)(budget / ((size_t)N * sizeof(cpx)));
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
-    cpx* scr;
-    GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)chunk * N * sizeof(cpx), (void**)&scr));
+    const bool two = d.two_stream_chunks && batch >= 4 * chunk;
+    cpx* scr0;
+    GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)(two ? 2 : 1) * chunk * N * sizeof(cpx), (void**)&scr0));
     const bool real_in = ops.ld_flags & LD_REAL;
-    for (long long b0 = 0; b0 < batch; b0 += chunk) {
+    ForkJoin fj(d, st, two);
+    long long ci = 0;
+    for (long long b0 = 0; b0 < batch; b0 += chunk, ci++) {
         long long nb = batch - b0 < chunk ? batch - b0 : chunk;
+        cudaStream_t st = fj.stream(ci);
+        cpx* scr = scr0 + (two && (ci & 1) ? (size_t)chunk * N : 0);
         // pass 1: columns n2 of every transform, length N1, twiddle w_N^(n2*k1) on store; the intermediate
         // is tile-major (T adjacent columns = one contiguous block) so these stores are fully coalesced
         const bool lean32 = d.w32 >= 1 && d.w32 <= 6 && !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
@@ -660,14 +692,21 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         const long long R1 = 1LL << l1, R2 = 1LL << l2;
         TwiddleTable tw;
         GD_TRY(d.twiddles(lg, &tw));
-        long long cb = (long long)(d.pass_scratch_budget / ((size_t)len * sizeof(cpx)));
+        // blocks sized to stay in L2 between the passes, alternating between two streams (see fft_pow2)
+        const size_t budget = d.pass_scratch_budget < d.l2_block_budget ? d.pass_scratch_budget : d.l2_block_budget;
+        long long cb = (long long)(budget / ((size_t)len * sizeof(cpx)));
         if (cb < 8) cb = 8;
         if (cb > s) cb = s;
-        cpx* scr;
-        GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)len * cb * sizeof(cpx), (void**)&scr));
+        const bool two = d.two_stream_chunks && outer * ((s + cb - 1) / cb) >= 4;
+        cpx* scr0;
+        GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)(two ? 2 : 1) * len * cb * sizeof(cpx), (void**)&scr0));
+        ForkJoin fj(d, st, two);
+        long long ci = 0;
         for (long long o = 0; o < outer; o++)
-            for (long long c0 = 0; c0 < s; c0 += cb) {
+            for (long long c0 = 0; c0 < s; c0 += cb, ci++) {
                 long long nc = s - c0 < cb ? s - c0 : cb;
+                cudaStream_t st = fj.stream(ci);
+                cpx* scr = scr0 + (two && (ci & 1) ? (size_t)len * cb : 0);
                 const cpx* sp = src + o * len * s + c0;
                 cpx* dp = dst + o * len * s + c0;
                 // pass 1: lines (n2, c): length R1 over n1 (stride R2*s); out block[(k1*R2 + n2)][c]

@@ -62,7 +62,7 @@ struct BluesteinPlan {      // fft/bluestein.go:26-65 cache, plus the cached FFT
     cpx* bhat = nullptr;        // FFT_la(b), la entries
 };
 
-enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OUT, SCR_PWELCH, SCR_AUX, SCR_CNT, SCR_TMA, SCR_NSLOTS };
+enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OUT, SCR_PWELCH, SCR_AUX, SCR_CNT, SCR_TMA, SCR_PROF, SCR_NSLOTS };
 
 struct Device {
     int dev = -1;
@@ -71,12 +71,16 @@ struct Device {
     cudaStream_t stream = nullptr;       // compute stream of the host-pointer entry points
     cudaStream_t stream_in = nullptr;    // H2D
     cudaStream_t stream_out = nullptr;   // D2H
+    cudaStream_t stream_aux = nullptr;   // every other L2-sized chunk of a multi-pass transform (ForkJoin, engine.cu)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cpx* wl[13] = {nullptr};             // intra-line tables exp(-2 pi i e/L), L = 2^k
     std::map<int, TwiddleTable> tw;      // keyed by log2 M
     std::map<long long, BluesteinPlan> blue;
     void* scratch[SCR_NSLOTS] = {nullptr};
     size_t scratch_bytes[SCR_NSLOTS] = {0};
-    size_t pass_scratch_budget = 1ull << 30;    // inter-pass scratch of the two-launch four-step path (chunk of transforms)
+    size_t pass_scratch_budget = 1ull << 30;    // upper bound of the inter-pass scratch of the two-launch four-step path
+    size_t l2_block_budget = 32ull << 20;       // inter-pass block of one chunk: small enough to stay in L2 between the passes
+    bool two_stream_chunks = true;              // alternate chunks between two streams
     bool wide_tiles = false;             // 512-thread tiles for L >= 1024
     int w32 = 2;                         // 1024-point lean passes: 32 points per thread (fft_w32.cuh); 0 = 16-point kernel
     bool debug_alias = false;            // timing experiment only: all transforms of a batch alias one buffer (results are garbage)
@@ -90,10 +94,10 @@ struct Device {
     bool use_fused = false;              // one persistent kernel for both four-step passes (N = L*L), L2-resident scratch
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)
-    int tma_two_queues = 0;              // separate in-order queues for pass-1 / pass-2 tiles (measured slower: the P1/P2 mix per SM drifts)
-    bool tma_p1_bulk = true;             // pass-1 output through the async proxy (staged bulk stores, published on completion)
-    int tma_dbg = 0;                     // bisecting switches of the fused kernel (bit 0: acquire load instead of fence, bit 1: unsplit drain, bit 2: no fence by the storing warps, bit 3: writer-side proxy fence)
-    int tma_delay = 1;                   // phases between P1(g) and P2(g); delay + 2 slots of 16 MiB must stay in L2
+    int tma_opt = 0;                     // measurement switches of the fused kernel (TmaFusedParams::opt)
+    int tma_prof = 0;                    // measurement: cycle counters of the fused kernel (gd_tma_profile_read)
+    int tma_delay = 2;                   // P1 phases the schedule runs ahead of P2 (fft_tma.cuh)
+    int tma_slots = 3;                   // scratch slots of 16 MiB (one transform each) kept in L2; delay <= slots - 1
     // The scratch blocks, dependency counters and the persisting L2 window are per device, not per stream: a call on
     // another stream first waits (on the device) for the previous user, see ScratchOrder.
     cudaEvent_t scratch_evt = nullptr;

@@ -91,12 +91,15 @@ __device__ __forceinline__ void dft16(cpx* v) {
         v[k1 * S] = r[0]; v[(k1 + 4) * S] = r[1]; v[(k1 + 8) * S] = r[2]; v[(k1 + 12) * S] = r[3];
     }
 }
+}  // namespace gd
+#include "fft_codelets.cuh"      // generated FMA-form codelets (tools/gen_codelets.py): dft8_fma 52, dft16_fma 144, dft32_fma 376 instructions
+namespace gd {
 template <int R, int S>
 __device__ __forceinline__ void dft(cpx* v) {
     if constexpr (R == 2) dft2<S>(v);
     else if constexpr (R == 4) dft4<S>(v);
-    else if constexpr (R == 8) dft8<S>(v);
-    else if constexpr (R == 16) dft16<S>(v);
+    else if constexpr (R == 8) dft8_fma<S>(v);       // 52 FP64 instructions (hand-written dft8 above: 64)
+    else if constexpr (R == 16) dft16_fma<S>(v);     // 144 (dft16 above: 160)
 }
 
 // v[r*S] *= w^r for r = 1..R-1, powers built by squaring/products from w (depth <= 4 multiplies).

@@ -32,19 +32,8 @@ __device__ __forceinline__ cpx mul_w32(cpx a) {
 }
 
 // forward 32-point DFT in registers, natural order in and out: v[k] = sum_n v[n] w32^(n k)
-// 2 x 16 decimation in time: even / odd inputs -> two 16-point DFTs -> w32^k -> radix-2
 __device__ __forceinline__ void dft32(cpx (&v)[32]) {
-    cpx e[16], o[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
-    dft16<1>(e);
-    dft16<1>(o);
-    o[1] = mul_w32<1>(o[1]);   o[2] = mul_w32<2>(o[2]);   o[3] = mul_w32<3>(o[3]);   o[4] = mul_w32<4>(o[4]);
-    o[5] = mul_w32<5>(o[5]);   o[6] = mul_w32<6>(o[6]);   o[7] = mul_w32<7>(o[7]);   o[8] = mul_w32<8>(o[8]);
-    o[9] = mul_w32<9>(o[9]);   o[10] = mul_w32<10>(o[10]); o[11] = mul_w32<11>(o[11]); o[12] = mul_w32<12>(o[12]);
-    o[13] = mul_w32<13>(o[13]); o[14] = mul_w32<14>(o[14]); o[15] = mul_w32<15>(o[15]);
-#pragma unroll
-    for (int k = 0; k < 16; k++) { v[k] = cadd(e[k], o[k]); v[k + 16] = csub(e[k], o[k]); }
+    dft32_fma(v);                                // generated FMA-form codelet (tools/gen_codelets.py): 376 FP64 instructions
 }
 
 // v[r] *= t0 * s^r, r = 0..31: four interleaved product chains (depth 8 instead of 31)

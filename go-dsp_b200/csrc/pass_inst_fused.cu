@@ -5,7 +5,8 @@ namespace gd {
 template <int LOG2L, int T>
 static cudaError_t launch_fused_impl(const FusedParams& a, long long total_items, int num_sms, cudaStream_t st) {
     using SH = PassShape<LOG2L>;
-    static KernelInfo info;
+    static KernelInfoPerDevice per_dev;
+    KernelInfo& info = per_dev.current();
     auto kern = fft_fused_kernel<LOG2L, T>;
     if (!info.ready) {
         info.threads = T * SH::P;

@@ -40,25 +40,33 @@ static Status tma_map(TmaEncodeFn enc, const void* base, long long count, long l
     return GD_OK;
 }
 
-bool tma_fused_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist) {
-    // TMA needs 16-byte aligned bases and pitches (always true for complex128) and pitches below 2^40 bytes
-    return ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && in_dist >= (long long)TMA_L * TMA_L &&
+bool tma_fused_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, int ld_conj, int st_conj, double scale) {
+    // forward (no hooks) or inverse (conj . forward . conj, scale folded into the twiddle); TMA needs 16-byte aligned
+    // bases and pitches (always true for complex128) and pitches below 2^40 bytes
+    const bool fwd = !ld_conj && !st_conj && scale == 1.0, inv = ld_conj && st_conj;
+    return (fwd || inv) && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && in_dist >= (long long)TMA_L * TMA_L &&
            out_dist >= (long long)TMA_L * TMA_L && in_dist < (1LL << 36) && out_dist < (1LL << 36);
 }
 
-// batched forward butterflies of N = 2^20 points; direction / scaling are expressed by ld_conj, st_conj, scale
+template <bool INV, bool PROF>
+static cudaError_t launch_one(int grid, const CUtensorMap& mx, const CUtensorMap& mi, const CUtensorMap& mo, const TmaFusedParams& f,
+                              cudaStream_t st) {
+    // the attribute is per device: set it on every call (cheap), a process may drive several GPUs
+    cudaError_t e = cudaFuncSetAttribute(fft_tma_fused_kernel<INV, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM);
+    if (e != cudaSuccess) return e;
+    fft_tma_fused_kernel<INV, PROF><<<grid, TMA_THREADS, TMA_SMEM, st>>>(mx, mi, mo, f);
+    return cudaGetLastError();
+}
+
+// batched butterflies of N = 2^20 points; inverse = (ld_conj, st_conj, scale = 1/N)
 Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long batch, int ld_conj,
                     int st_conj, double scale, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GD_CUDA(cudaFuncSetAttribute(fft_tma_fused2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
-        GD_CUDA(cudaFuncSetAttribute(fft_tma_fused2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA2_SMEM));
-        attr_set = true;
-    }
+    const bool inv = ld_conj && st_conj;
     TmaEncodeFn enc;
     GD_TRY(tma_encoder(&enc));
     const long long N = (long long)TMA_L * TMA_L;
-    const int D = d.tma_delay, S = D + 2;
+    const int S = d.tma_slots;
+    const int D = d.tma_delay < S - 1 ? d.tma_delay : S - 1;      // P2(g - S) must precede P1(g) in the sequence: D <= S - 1
     TwiddleTable tw;
     GD_TRY(d.twiddles(20, &tw));
     cpx* scratch;
@@ -67,6 +75,11 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
     const long long CH = 128;               // transforms per launch: one tensor map per array, item ids stay small
     int* cnt;
     GD_TRY(d.ensure_scratch(SCR_CNT, (2 * (size_t)CH + 2) * sizeof(int), (void**)&cnt));
+    long long* prof = nullptr;
+    if (d.tma_prof) {
+        GD_TRY(d.ensure_scratch(SCR_PROF, (size_t)d.num_sms * TMA_PROF_SLOTS * sizeof(long long), (void**)&prof));
+        GD_CUDA(cudaMemsetAsync(prof, 0, (size_t)d.num_sms * TMA_PROF_SLOTS * sizeof(long long), st));
+    }
     CUtensorMap m_int;
     GD_TRY(tma_map(enc, scratch, S, N, &m_int));
     // keep the scratch slots resident in L2: persisting access-policy window while the launches run
@@ -99,17 +112,15 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
         f.batch = (int)nb; f.delay = D; f.nslots = S; f.scratch = scratch;
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.wl = d.wl[10]; f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.tw_log2m = 20;
-        f.ld_conj = ld_conj; f.st_conj = st_conj; f.scale = scale;
-        f.two_queues = d.tma_two_queues;
-        f.hints = d.tma_p1_bulk ? 1 : 0;        // evict-last on the bulk stores of Int: without it they crawl under the persisting window
-        f.dbg_acqload = d.tma_dbg & 1; f.dbg_nosplit = (d.tma_dbg >> 1) & 1; f.dbg_nopubfence = (d.tma_dbg >> 2) & 1; f.dbg_wproxy = (d.tma_dbg >> 3) & 1;
+        f.scale = scale;
+        f.opt = d.tma_opt;
+        f.prof = prof;
         cudaError_t e = cudaMemsetAsync(cnt, 0, (2 * (size_t)CH + 2) * sizeof(int), st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(counters)"); break; }
         const long long nitems = 2 * nb * (TMA_L / TMA_T);
         const int grid = (int)(nitems < d.num_sms ? nitems : d.num_sms);
-        if (d.tma_p1_bulk) fft_tma_fused2_kernel<true><<<grid, TMA_THREADS, TMA2_SMEM, st>>>(m_x, m_int, m_out, f);
-        else fft_tma_fused2_kernel<false><<<grid, TMA_THREADS, TMA2_SMEM, st>>>(m_x, m_int, m_out, f);
-        e = cudaGetLastError();
+        if (prof) e = inv ? launch_one<true, true>(grid, m_x, m_int, m_out, f, st) : launch_one<false, true>(grid, m_x, m_int, m_out, f, st);
+        else e = inv ? launch_one<true, false>(grid, m_x, m_int, m_out, f, st) : launch_one<false, false>(grid, m_x, m_int, m_out, f, st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "fft_tma_fused_kernel launch"); break; }
         g_launches++;
     }

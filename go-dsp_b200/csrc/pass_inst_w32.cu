@@ -4,7 +4,8 @@ namespace gd {
 
 template <int T, int MINB, bool STAGED>
 static cudaError_t launch_pass32_impl(const PassParams& a, int num_sms, cudaStream_t st) {
-    static KernelInfo info;
+    static KernelInfoPerDevice per_dev;
+    KernelInfo& info = per_dev.current();
     auto kern = fft_pass32_kernel<T, MINB, STAGED>;
     if (!info.ready) {
         info.threads = 32 * T;

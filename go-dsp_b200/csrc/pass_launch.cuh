@@ -12,6 +12,18 @@ struct KernelInfo {
     int smem = 0;
     int threads = 0;
 };
+// The dynamic shared-memory opt-in (cudaFuncSetAttribute) and the occupancy are per DEVICE, and one process may drive
+// several GPUs (gd_init(ndev), gd_use_device): one slot per device, filled on first use on that device. Callers hold
+// their device's mutex, so a slot is only ever touched by one thread at a time.
+constexpr int GD_MAX_DEVICES = 16;
+struct KernelInfoPerDevice {
+    KernelInfo slot[GD_MAX_DEVICES];
+    KernelInfo& current() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return slot[dev >= 0 && dev < GD_MAX_DEVICES ? dev : 0];
+    }
+};
 
 // one launcher per (LOG2L, T); `wide` picks the 512-thread variant where one exists.
 typedef cudaError_t (*PassLauncher)(const PassParams&, bool generic, int num_sms, cudaStream_t);
@@ -19,7 +31,8 @@ typedef cudaError_t (*PassLauncher)(const PassParams&, bool generic, int num_sms
 template <int LOG2L, int T, bool GENERIC>
 cudaError_t launch_pass_impl(const PassParams& a, int num_sms, cudaStream_t st) {
     using SH = PassShape<LOG2L>;
-    static KernelInfo info;      // one per instantiation; benign race (idempotent values)
+    static KernelInfoPerDevice per_dev;      // one per instantiation
+    KernelInfo& info = per_dev.current();
     auto kern = fft_pass_kernel<LOG2L, T, GENERIC>;
     if (!info.ready) {
         info.threads = T * SH::P;

@@ -175,8 +175,8 @@ static Status launch_fused(Device& d, const double* x, long long nfft, long long
     const bool aligned = (reinterpret_cast<uintptr_t>(x + seg0 * stride) & 15) == 0;
     auto kern = aligned ? pwelch_fused_kernel<LOG2L, true> : pwelch_fused_kernel<LOG2L, false>;
     const int threads = SH::T * SH::P, smem = SH::T * SH::LS * (int)sizeof(cpx);
-    static int bps[2] = {0, 0};
-    int& blocks_per_sm = bps[aligned ? 1 : 0];
+    static int bps[2][16] = {{0}};                       // per (variant, device): the opt-in below is a per-device attribute
+    int& blocks_per_sm = bps[aligned ? 1 : 0][d.dev & 15];
     if (!blocks_per_sm) {
         GD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int b = 0;

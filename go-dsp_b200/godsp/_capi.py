@@ -44,6 +44,7 @@ SIGNATURES = {
     "gd_pwelch_partial_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "gd_pwelch_finalize_dev": (_int, [_vp, _i64, _i64, C.c_double, _vp, _vp]),
     "gd_kernel_launches": (_i64, []),
+    "gd_tma_profile_read": (_int, [_vp, _int]),
 }
 
 _lib = None

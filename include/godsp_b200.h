@@ -139,6 +139,10 @@ GD_API int gd_pwelch_partial_dev(const double* x_dev, int64_t nfft, int64_t nove
 GD_API int gd_pwelch_finalize_dev(const double* raw_dev, int64_t lp, int64_t nsegs, double norm, double* pxx_dev, void* stream);
 /* number of kernels this library has launched on the calling thread's device since gd_init */
 GD_API int64_t gd_kernel_launches(void);
+/* Measurement only: after gd_set_option("tma_prof", 1) the fused 2^20 kernel keeps 32 cycle counters per CTA (where its
+ * loader, storers and consumer groups waited); copies up to max_ctas * 32 values of the last launch to `out` and returns
+ * the number of CTAs, or a negative status. */
+GD_API int gd_tma_profile_read(int64_t* out, int max_ctas);
 
 #ifdef __cplusplus
 }

@@ -149,10 +149,10 @@ def test_batched(gd, b, lg):
     assert rel_l2(out, x) <= TOL
 
 
-SCHEDULE_DEFAULTS = {"tma": 1, "tma_delay": 1, "tma_p1_bulk": 1, "fused": 0, "wide_tiles": 0, "pass_scratch_mb": 1024, "w32": 2}
+SCHEDULE_DEFAULTS = {"tma": 1, "tma_delay": 2, "tma_slots": 3, "tma_opt": 0, "fused": 0, "wide_tiles": 0, "pass_scratch_mb": 1024, "w32": 2}
 
 
-@pytest.mark.parametrize("opts", [{"tma": 1}, {"tma": 1, "tma_delay": 2}, {"tma": 1, "tma_delay": 0}, {"tma": 1, "tma_p1_bulk": 0}, {"tma": 0},
+@pytest.mark.parametrize("opts", [{"tma": 1}, {"tma": 1, "tma_delay": 1}, {"tma": 1, "tma_delay": 0}, {"tma": 1, "tma_delay": 3, "tma_slots": 4}, {"tma": 1, "tma_delay": 1, "tma_slots": 2}, {"tma": 1, "tma_opt": 2}, {"tma": 0},
                                   {"tma": 0, "fused": 1}, {"tma": 0, "wide_tiles": 1}, {"tma": 0, "pass_scratch_mb": 16},
                                   {"tma": 0, "w32": 0}, {"tma": 0, "w32": 5}])
 def test_alternative_schedules_agree(gd, opts):   # every planner variant of the 2^20-point transform must give the same result
@@ -185,7 +185,7 @@ def test_fft_batch_api(gd, n, b):                 # additive FFTBatch of the shi
         godsp.fft.FFTBatch(x[:-1], n)
 
 
-@pytest.mark.parametrize("delay", [1, 2])
+@pytest.mark.parametrize("delay", [2, 1])
 def test_tma_fused_stress(gd, delay):             # race hunt: every row of every repetition must keep its energy (Parseval)
     _, capi, L = gd
     import torch
@@ -205,7 +205,7 @@ def test_tma_fused_stress(gd, delay):             # race hunt: every row of ever
             ey = (y.view(nb, -1) ** 2).sum(1)
             assert float(((ey / n - ex).abs() / ex).max()) < 1e-13
     finally:
-        capi.check(L.gd_set_option(b"tma_delay", 1))
+        capi.check(L.gd_set_option(b"tma_delay", SCHEDULE_DEFAULTS["tma_delay"]))
 
 
 def test_tma_fused_chunking(gd):                  # more than one 128-transform launch, a partial last chunk, in place

@@ -25,7 +25,7 @@ while args and args[0].startswith("--"):
     elif k == "--log2n": log2n = v
 combos = args or ["w32=0"]
 DEFAULTS = {"w32": 1, "fused": 0, "tiled_scratch": 0, "wide_tiles": 0, "pass_scratch_mb": 1024, "fused_delay": 2,
-            "fused_slot_mb": 16, "l2_window": 1, "debug_alias": 0, "tma": 1, "tma_delay": 1, "tma_dbg": 0, "tma_two_queues": 0, "tma_p1_bulk": 1}
+            "fused_slot_mb": 16, "l2_window": 1, "debug_alias": 0, "tma": 1, "tma_delay": 2, "tma_slots": 3, "tma_opt": 0}
 
 L = capi.lib()
 capi.check(L.gd_use_device(0))

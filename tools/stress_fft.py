@@ -18,7 +18,7 @@ y = torch.empty_like(x)
 capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), batch * n * 2, 3, 0, None)); capi.check(L.gd_stream_sync(None))
 ex = (x.view(batch, -1) ** 2).sum(1)
 for combo in (args or [""]):
-    for k0, v0 in {"tma": 1, "tma_delay": 1, "tma_dbg": 0, "tma_two_queues": 0, "tma_p1_bulk": 1}.items():
+    for k0, v0 in {"tma": 1, "tma_delay": 2, "tma_slots": 3, "tma_opt": 0}.items():
         capi.check(L.gd_set_option(k0.encode(), v0))
     for kv in combo.split(","):
         if kv:

@@ -8,7 +8,7 @@
 #include <vector>
 #include <complex>
 #include <algorithm>
-#include "fft_tma.cuh"
+#include "fft_tma_legacy.cuh"
 using namespace gd;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
