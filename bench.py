@@ -416,6 +416,22 @@ def run_ours(args):
         del hin_np, hout_np
         L.gd_pinned_free(hin)
         L.gd_pinned_free(hout)
+        # the same call on PAGEABLE host memory -- what fft.FFT(x) on a plain Go slice hands the library: chunks go through
+        # the library's pinned staging ring, filled / drained by host threads
+        pb = min(eb, 64)
+        pin_np = np.empty(pb * n * 2)
+        capi.check(L.gd_memcpy_d2h(pin_np.ctypes.data, x.data_ptr(), pb * n * 16))
+        pout_np = np.empty(pb * n * 2)
+
+        def e2e_pageable_step():
+            capi.check(L.gd_fft_batch_c2c(pin_np.ctypes.data, pout_np.ctypes.data, n, pb, 1))
+
+        pms = timed_host(e2e_pageable_step, args.e2e_steps, 1)
+        line["e2e_pageable"] = {"value": pb * n * world / (pms * 1e-3) / 1e9, "unit": "GS/s", "ms_per_step": pms, "batch_per_gpu": pb,
+                                "h2d_bytes_per_step": pb * n * 16, "d2h_bytes_per_step": pb * n * 16,
+                                "matches_device_path": bool(np.array_equal(pout_np[: 2 * n], ref)),
+                                "api": "gd_fft_batch_c2c on pageable numpy buffers (pinned staging ring + host copy threads inside the library)"}
+        del pin_np, pout_np
 
     # ---------------- FFT: CPU baseline (rank 0, N = 1 only)
     if "cpu" not in skip and world == 1:

@@ -136,7 +136,7 @@ Status Device::ensure_scratch(ScratchSlot s, size_t bytes, void** out) {
 }
 
 Status Device::l2_release() {
-    if (l2_dirty) {
+    if (l2_dirty && !l2_hold) {
         GD_CUDA(cudaCtxResetPersistingL2Cache());
         GD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
         l2_carved = 0;
@@ -193,17 +193,73 @@ static PassParams base_params(Device& d, int log2l) {
 struct ForkJoin {
     Device& d;
     cudaStream_t st;
-    bool on;
+    bool on, window = false;
     ForkJoin(Device& dev, cudaStream_t s, bool enable) : d(dev), st(s), on(enable && dev.stream_aux && s != dev.stream_aux) {
         if (on) { cudaEventRecord(d.ev_fork, st); cudaStreamWaitEvent(d.stream_aux, d.ev_fork, 0); }
     }
     cudaStream_t stream(long long i) const { return on && (i & 1) ? d.stream_aux : st; }
+    // keep the inter-pass blocks in L2: persisting access-policy window over the scratch on the streams of this call
+    void persist(void* base, size_t bytes) {
+        if (!d.l2_block_window || !d.use_l2_window || d.l2_persist_max == 0 || d.l2_window_max == 0) return;
+        const size_t want = bytes < d.l2_persist_max ? bytes : d.l2_persist_max;
+        if (d.l2_carved != want) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return; }
+            d.l2_carved = want;
+        }
+        set(base, bytes < d.l2_window_max ? bytes : d.l2_window_max, (double)want);
+        window = true;
+        d.l2_hold = true;                    // launch_pass must not hand the set-aside back between the chunks
+    }
+    void set(void* base, size_t bytes, double carved) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = base;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        if (bytes) {
+            const double ratio = carved / (double)bytes;
+            attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        }
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        if (on) cudaStreamSetAttribute(d.stream_aux, cudaStreamAttributeAccessPolicyWindow, &attr);
+    }
     ~ForkJoin() {
+        if (window) { set(nullptr, 0, 0.0); d.l2_hold = false; d.l2_dirty = true; }
         if (on) { cudaEventRecord(d.ev_join, d.stream_aux); cudaStreamWaitEvent(st, d.ev_join, 0); }
     }
 };
 
 // ------------------------------------------------------------------ power-of-two transforms
+static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st);
+Status transpose_batched(const cpx* in, cpx* out, long long batch, long long rows, long long cols, cudaStream_t st);
+
+// N = 2^25 .. 2^34 on one GPU: an outer four-step over the building blocks below 2^24 (the reference has no length limit,
+// fft/fft.go:72-87). x as a row-major [N1][N2] matrix: (1) every column, length N1, strided lines; (2) w_N^(n2 k1), phases
+// by sincospi of exactly reduced exponents; (3) every row, length N2; (4) X[k1 + N1 k2] = result[k1][k2]: one transpose.
+// Forward and inverse (every sub-step inverted, conjugate twiddle) only; needs a second N-element buffer.
+static Status fft_pow2_huge(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, int log2n, long long batch,
+                            const FusedOps& ops, cudaStream_t st) {
+    const bool fwd = ops.ld_flags == 0 && ops.st_flags == 0;
+    const bool inv = ops.ld_flags == LD_CONJ && ops.st_flags == (ST_CONJ | ST_SCALE);
+    if (!fwd && !inv) return invalid("transforms above 2^24 points support plain forward / inverse only (no Bluestein above a padded length of 2^24)");
+    if (log2n > 34) return invalid("fft_pow2: N > 2^34");
+    const int dir = inv ? -1 : +1;
+    const int l1 = (log2n + 1) / 2, l2 = log2n - l1;
+    const long long N = 1LL << log2n, N1 = 1LL << l1, N2 = 1LL << l2;
+    cpx* tmp;
+    GD_TRY(d.ensure_scratch(SCR_HUGE, (size_t)N * sizeof(cpx), (void**)&tmp));
+    for (long long b = 0; b < batch; b++) {
+        const cpx* src = (const cpx*)in + b * in_dist;
+        cpx* dst = out + b * out_dist;
+        GD_TRY(fft_axis(d, src, tmp, 1, N1, N2, dir, st));                       // (1) columns: lines over n1, stride N2
+        GD_TRY(fourstep_twiddle(tmp, N1, N2, 0, 0, log2n, st, dir));             // (2)
+        GD_TRY(fft1d(d, tmp, N2, tmp, N2, N2, N1, false, dir, st));              // (3) rows, in place
+        GD_TRY(transpose_batched(tmp, dst, 1, N1, N2, st));                      // (4)
+    }
+    return GD_OK;
+}
+
 Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, int log2n,
                 long long batch, const FusedOps& ops, cudaStream_t st) {
     if (log2n < 1 || batch < 1) return invalid("fft_pow2: bad size");
@@ -220,7 +276,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         p.scale = ops.scale; p.div = ops.div;
         return launch_pass(d, log2n, p, st);
     }
-    if (log2n > 24) return invalid("fft_pow2: N > 2^24 needs the multi-GPU path");
+    if (log2n > 24) return fft_pow2_huge(d, in, in_dist, out, out_dist, log2n, batch, ops, st);
     const bool lean = !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
     if (d.use_tma && lean && log2n == 20 && !d.debug_alias) {
         const int lc = (ops.ld_flags & LD_CONJ) ? 1 : 0, sc = (ops.st_flags & ST_CONJ) ? 1 : 0;
@@ -302,6 +358,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
     GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)(two ? 2 : 1) * chunk * N * sizeof(cpx), (void**)&scr0));
     const bool real_in = ops.ld_flags & LD_REAL;
     ForkJoin fj(d, st, two);
+    if (batch > chunk) fj.persist(scr0, (size_t)(two ? 2 : 1) * chunk * N * sizeof(cpx));
     long long ci = 0;
     for (long long b0 = 0; b0 < batch; b0 += chunk, ci++) {
         long long nb = batch - b0 < chunk ? batch - b0 : chunk;
@@ -397,7 +454,7 @@ __global__ void splitmix_kernel(double* out, long long n, unsigned long long see
 // block[r][c] *= w_N^((row0 + r) * (col0 + c)), N = 2^log2n <= 2^40. One thread owns 16 consecutive c of a row:
 // base and step come from sincospi of exactly reduced exponents, the run by a 15-term product chain.
 __global__ void fourstep_twiddle_kernel(cpx* __restrict__ blk, long long rows, long long cols, long long row0,
-                                        long long col0, int log2n) {
+                                        long long col0, int log2n, double sgn) {
     const long long runs_per_row = (cols + 15) / 16;
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= rows * runs_per_row) return;
@@ -405,9 +462,9 @@ __global__ void fourstep_twiddle_kernel(cpx* __restrict__ blk, long long rows, l
     const unsigned long long mask = (1ULL << log2n) - 1ULL, gr = (unsigned long long)(row0 + r);
     const double invn = 1.0 / (double)(1ULL << log2n);
     double s, co;
-    sincospi(-2.0 * (double)((gr * (unsigned long long)(col0 + c)) & mask) * invn, &s, &co);
+    sincospi(sgn * 2.0 * (double)((gr * (unsigned long long)(col0 + c)) & mask) * invn, &s, &co);
     cpx w = make_double2(co, s);
-    sincospi(-2.0 * (double)(gr & mask) * invn, &s, &co);
+    sincospi(sgn * 2.0 * (double)(gr & mask) * invn, &s, &co);
     const cpx step = make_double2(co, s);
     cpx* p = blk + r * cols + c;
     const int n = (int)(cols - c < 16 ? cols - c : 16);
@@ -447,7 +504,7 @@ __global__ void __launch_bounds__(256) transpose_batched_kernel(const cpx* __res
 Status transpose_batched(const cpx* in, cpx* out, long long batch, long long rows, long long cols, cudaStream_t st) {
     if (batch < 1 || rows < 1 || cols < 1 || in == out) return invalid("transpose_batched: bad arguments");
     const long long gx = (cols + 31) / 32, gy = (rows + 31) / 32;
-    if (gy > 65535 || batch > 65535) return invalid("transpose_batched: grid too large");
+    if (gy > 65535 || batch > 65535) return invalid("transpose_batched: grid too large");      // rows <= 2^21
     transpose_batched_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)batch), 256, 0, st>>>(in, out, rows, cols);
     g_launches++;
     GD_CUDA(cudaGetLastError());
@@ -539,10 +596,10 @@ Status peer_block_copy(const cpx* src, cpx* const* peers, int world, int rank, l
     return GD_OK;
 }
 
-Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st) {
+Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st, int dir) {
     if (rows < 1 || cols < 1 || log2n < 1 || log2n > 40) return invalid("fourstep_twiddle: bad arguments");
     long long threads = rows * ((cols + 15) / 16);
-    fourstep_twiddle_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(blk, rows, cols, row0, col0, log2n);
+    fourstep_twiddle_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(blk, rows, cols, row0, col0, log2n, dir < 0 ? 1.0 : -1.0);
     g_launches++;
     GD_CUDA(cudaGetLastError());
     return GD_OK;
@@ -657,18 +714,84 @@ Status convolve(Device& d, const cpx* x, const cpx* y, cpx* out, long long n, cu
     cpx *X, *Y;
     GD_TRY(d.ensure_scratch(SCR_B, (size_t)n * sizeof(cpx), (void**)&X));
     GD_TRY(d.ensure_scratch(SCR_C, (size_t)n * sizeof(cpx), (void**)&Y));
-    GD_TRY(fft1d(d, x, n, X, n, n, 1, false, +1, st));
     GD_TRY(fft1d(d, y, n, Y, n, n, 1, false, +1, st));
-    pointwise_mul_kernel<<<grid_for(n, 256), 256, 0, st>>>(X, Y, n);
-    g_launches++;
-    GD_CUDA(cudaGetLastError());
+    if (is_pow2(n) && n >= 2 && n <= (1LL << 24)) {
+        // FFT(x) * FFT(y) (fft.go:63-66) fused into the store of FFT(x): ST_MULAUX with aux = FFT(y)
+        FusedOps f;
+        f.st_flags = ST_MULAUX; f.aux_out = Y;
+        GD_TRY(fft_pow2(d, x, n, X, n, ilog2ll(n), 1, f, st));
+    } else {
+        GD_TRY(fft1d(d, x, n, X, n, n, 1, false, +1, st));
+        pointwise_mul_kernel<<<grid_for(n, 256), 256, 0, st>>>(X, Y, n);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+    }
     return fft1d(d, X, n, out, n, n, 1, false, -1, st);
+}
+
+// ------------------------------------------------------------------ linear convolution (overlap-save)
+// xe[i] = x[i - lead] for lead <= i < lead + nx, else 0
+__global__ void ols_extend_kernel(const cpx* __restrict__ x, long long nx, long long lead, long long total, cpx* __restrict__ xe) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long j = i - lead;
+    xe[i] = (j >= 0 && j < nx) ? x[j] : make_double2(0.0, 0.0);
+}
+// out[b*step + j] = blocks[b*lb + lead + j], j < step: the part of every circular block result that is free of wrap-around
+__global__ void ols_take_kernel(const cpx* __restrict__ blocks, long long b0, long long nb, long long lb, long long lead, long long step,
+                                long long nout, cpx* __restrict__ out) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= nb * step) return;
+    const long long b = t / step, j = t - b * step, o = (b0 + b) * step + j;
+    if (o < nout) out[o] = blocks[b * lb + lead + j];
+}
+
+// Linear convolution y[n] = sum_m h[m] x[n - m], n < nx + nh - 1, as circular convolutions of length lb on blocks of x that
+// overlap by nh - 1 samples (overlap-save). Each block is what fft.Convolve computes (fft/fft.go:55-69: IFFT(FFT(a) * FFT(b)))
+// with FFT(h) taken once; the overlapping blocks are read in place (rows `step` apart), the product with FFT(h) is fused
+// into the forward transform's store and conj / scale into the inverse.
+Status convolve_linear(Device& d, const cpx* x, long long nx, const cpx* h, long long nh, cpx* out, cudaStream_t st) {
+    if (!x || !h || !out || nx < 1 || nh < 1) return invalid("convolve_linear: bad arguments");
+    if (nh > nx) { const cpx* t = x; x = h; h = t; long long tn = nx; nx = nh; nh = tn; }      // convolution commutes: h is the short one
+    const long long nout = nx + nh - 1, lead = nh - 1;
+    if (nh > (1LL << 21)) return invalid("convolve_linear: the shorter operand must not exceed 2^21 points");
+    long long lb = 4096;
+    while (lb < 4 * nh) lb <<= 1;
+    if (nout <= lb) { lb = 2; while (lb < nout) lb <<= 1; }
+    int lg = 0;
+    while ((1LL << lg) < lb) lg++;
+    const long long step = lb - lead, nblocks = (nout + step - 1) / step, total = (nblocks - 1) * step + lb;
+    cpx *xe, *H, *A;
+    GD_TRY(d.ensure_scratch(SCR_B, (size_t)total * sizeof(cpx), (void**)&xe));
+    GD_TRY(d.ensure_scratch(SCR_C, (size_t)lb * sizeof(cpx), (void**)&H));
+    long long chunk = (long long)((256ull << 20) / ((size_t)lb * sizeof(cpx)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > nblocks) chunk = nblocks;
+    GD_TRY(d.ensure_scratch(SCR_A, (size_t)chunk * lb * sizeof(cpx), (void**)&A));
+    ols_extend_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, nx, lead, total, xe);
+    ols_extend_kernel<<<grid_for(lb, 256), 256, 0, st>>>(h, nh, 0, lb, H);
+    g_launches += 2;
+    GD_CUDA(cudaGetLastError());
+    FusedOps none;
+    GD_TRY(fft_pow2(d, H, lb, H, lb, lg, 1, none, st));                      // FFT(h), once
+    for (long long b0 = 0; b0 < nblocks; b0 += chunk) {
+        const long long nb = nblocks - b0 < chunk ? nblocks - b0 : chunk;
+        FusedOps f1;                                                         // A = FFT(block) * FFT(h)            (fft.go:60-66)
+        f1.st_flags = ST_MULAUX; f1.aux_out = H;
+        GD_TRY(fft_pow2(d, xe + b0 * step, step, A, lb, lg, nb, f1, st));
+        FusedOps f2;                                                         // IFFT: conj . FFT . conj, exact 1/lb (fft.go:35-52)
+        f2.ld_flags = LD_CONJ; f2.st_flags = ST_CONJ | ST_SCALE; f2.scale = 1.0 / (double)lb;
+        GD_TRY(fft_pow2(d, A, lb, A, lb, lg, nb, f2, st));
+        ols_take_kernel<<<grid_for(nb * step, 256), 256, 0, st>>>(A, b0, nb, lb, lead, step, nout, out);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+    }
+    return GD_OK;
 }
 
 // ------------------------------------------------------------------ N-d transforms
 // one axis: lines (o, i), o < outer, i < s, element stride s, length len. src may equal dst.
-static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir,
-                       cudaStream_t st) {
+static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st) {
     const long long nlines = outer * s;
     if (len == 1) {
         if (src != dst) GD_CUDA(cudaMemcpyAsync(dst, src, (size_t)nlines * sizeof(cpx), cudaMemcpyDeviceToDevice, st));
@@ -701,6 +824,7 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         cpx* scr0;
         GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)(two ? 2 : 1) * len * cb * sizeof(cpx), (void**)&scr0));
         ForkJoin fj(d, st, two);
+        if (outer * ((s + cb - 1) / cb) > 1) fj.persist(scr0, (size_t)(two ? 2 : 1) * len * cb * sizeof(cpx));
         long long ci = 0;
         for (long long o = 0; o < outer; o++)
             for (long long c0 = 0; c0 < s; c0 += cb, ci++) {

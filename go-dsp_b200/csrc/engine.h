@@ -62,7 +62,7 @@ struct BluesteinPlan {      // fft/bluestein.go:26-65 cache, plus the cached FFT
     cpx* bhat = nullptr;        // FFT_la(b), la entries
 };
 
-enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OUT, SCR_PWELCH, SCR_AUX, SCR_CNT, SCR_TMA, SCR_PROF, SCR_NSLOTS };
+enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OUT, SCR_PWELCH, SCR_AUX, SCR_CNT, SCR_TMA, SCR_PROF, SCR_HUGE, SCR_NSLOTS };
 
 struct Device {
     int dev = -1;
@@ -81,6 +81,8 @@ struct Device {
     size_t pass_scratch_budget = 1ull << 30;    // upper bound of the inter-pass scratch of the two-launch four-step path
     size_t l2_block_budget = 32ull << 20;       // inter-pass block of one chunk: small enough to stay in L2 between the passes
     bool two_stream_chunks = true;              // alternate chunks between two streams
+    bool l2_block_window = true;                // persisting L2 window over the inter-pass blocks of a chunked call
+    bool l2_hold = false;                       // a chunked call is in flight: keep the set-aside between its launches
     bool wide_tiles = false;             // 512-thread tiles for L >= 1024
     int w32 = 2;                         // 1024-point lean passes: 32 points per thread (fft_w32.cuh); 0 = 16-point kernel
     bool debug_alias = false;            // timing experiment only: all transforms of a batch alias one buffer (results are garbage)
@@ -143,14 +145,20 @@ Status fftn(Device& d, const cpx* in, cpx* out, const long long* dims, int nd, i
 
 // ---- Welch PSD -----------------------------------------------------------------------------
 // raw[k] (+)= sum over local segments of |FFT(w * seg)[k]|^2 folded to k < lp; segments seg0..seg0+nseg-1
-Status pwelch_partial(Device& d, const double* x, long long nfft, long long stride, long long fftlen,
+// fmt: 0 float64, 1 float32, 2 int16, 3 uint8 -- the PCM formats are decoded as wav.ReadFloats does (wav/wav.go:138-161)
+Status pwelch_partial(Device& d, const void* x, int fmt, long long nfft, long long stride, long long fftlen,
                       long long lp, long long seg0, long long nseg, const double* win, double* raw,
                       cudaStream_t st);
+// STFT / spectrogram: out[c][j] = FFT(win * segment c, zero-padded to fftlen)[j], j < lp  (spectral/pwelch.go:104-113 without the sum)
+Status stft(Device& d, const double* x, long long nfft, long long stride, long long fftlen, long long lp, long long seg0,
+            long long nseg, const double* win, cpx* out, cudaStream_t st);
+// linear (non-circular) convolution by overlap-save on top of the circular Convolve (fft/fft.go:55-69): out has nx + nh - 1 elements
+Status convolve_linear(Device& d, const cpx* x, long long nx, const cpx* h, long long nh, cpx* out, cudaStream_t st);
 // pxx[j] = raw[j] / nsegs (x2 for 0<j<lp-1) / norm      (spectral/pwelch.go:113-121,134-136)
 Status pwelch_finalize(const double* raw, long long lp, long long nsegs, double norm, double* pxx, cudaStream_t st);
 
 // ---- distributed four-step (C5) building blocks -------------------------------------------
-Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st);
+Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st, int dir = 1);
 Status repack_gkw(const cpx* in, cpx* out, long long G, long long K, long long W, cudaStream_t st);
 Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,
                          cudaStream_t st);

@@ -72,7 +72,7 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
     cpx* scratch;
     const size_t scr_bytes = (size_t)S * N * sizeof(cpx);
     GD_TRY(d.ensure_scratch(SCR_TMA, scr_bytes, (void**)&scratch));
-    const long long CH = 128;               // transforms per launch: one tensor map per array, item ids stay small
+    const long long CH = 512;               // transforms per launch (one tensor map per array; every launch ramps up and drains 3 phases)
     int* cnt;
     GD_TRY(d.ensure_scratch(SCR_CNT, (2 * (size_t)CH + 2) * sizeof(int), (void**)&cnt));
     long long* prof = nullptr;

@@ -14,6 +14,27 @@
 
 namespace gd {
 
+// Sample formats of the signal: float64, or the on-disk formats of wav/wav.go decoded exactly as
+// Wav.ReadFloats does (wav/wav.go:138-161, float32 arithmetic) and then widened, as a caller's float64(f) would:
+//   uint8:  float32(v) / 255            int16:  (float32(v) + 32768) / 65535            float32: as is
+enum : int { SMP_F64 = 0, SMP_F32 = 1, SMP_S16 = 2, SMP_U8 = 3 };
+__host__ __device__ __forceinline__ int sample_bytes(int fmt) { return fmt == SMP_F64 ? 8 : fmt == SMP_F32 ? 4 : fmt == SMP_S16 ? 2 : 1; }
+template <int FMT>
+__device__ __forceinline__ double load_sample(const void* __restrict__ x, long long i) {
+    if constexpr (FMT == SMP_F64) return __ldg(reinterpret_cast<const double*>(x) + i);
+    else if constexpr (FMT == SMP_F32) return (double)__ldg(reinterpret_cast<const float*>(x) + i);
+    else if constexpr (FMT == SMP_S16) return (double)__fdiv_rn((float)__ldg(reinterpret_cast<const short*>(x) + i) + 32768.0f, 65535.0f);
+    else return (double)__fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char*>(x) + i), 255.0f);
+}
+__device__ __forceinline__ double load_sample_rt(const void* __restrict__ x, long long i, int fmt) {
+    switch (fmt) {
+        case SMP_F32: return load_sample<SMP_F32>(x, i);
+        case SMP_S16: return load_sample<SMP_S16>(x, i);
+        case SMP_U8: return load_sample<SMP_U8>(x, i);
+    }
+    return load_sample<SMP_F64>(x, i);
+}
+
 template <int LOG2L>
 struct PwShape {
     static constexpr int L = 1 << LOG2L;
@@ -25,10 +46,13 @@ struct PwShape {
 // PREFETCH: the samples of the next segment pair (one contiguous range of stride + nfft doubles: the two
 // segments overlap) are copied with cp.async into the group's idle exchange buffer while the last
 // butterfly step and the |Z|^2 accumulation of the current pair run; needs 16-byte aligned ranges.
-template <int LOG2L, bool PREFETCH>
+// FMT: sample format; the decode is part of the segment load (PREFETCH stages raw float64 only).
+template <int LOG2L, bool PREFETCH, int FMT>
 __global__ void __launch_bounds__(PwShape<LOG2L>::T * PwShape<LOG2L>::P, 2)
-pwelch_fused_kernel(const double* __restrict__ x, long long nfft, long long stride, long long seg0, long long nseg,
+pwelch_fused_kernel(const void* __restrict__ xv, long long nfft, long long stride, long long seg0, long long nseg,
                     const double* __restrict__ win, double* __restrict__ partial, const cpx* __restrict__ wl) {
+    static_assert(!PREFETCH || FMT == SMP_F64, "the staged path copies float64 ranges");
+    const double* __restrict__ x = reinterpret_cast<const double*>(xv);
     using SH = PwShape<LOG2L>;
     constexpr int L = SH::L, P = SH::P, T = SH::T, LS = SH::LS;
     constexpr int NSTEP = PassShape<LOG2L>::NSTEP, LASTR = PassShape<LOG2L>::LASTR;
@@ -89,16 +113,15 @@ pwelch_fused_kernel(const double* __restrict__ x, long long nfft, long long stri
                 z[i] = make_double2(w * a, w * b);
             }
         } else {
-            const double* xa = x + (seg0 + 2 * u) * stride;
-            const double* xb = xa + stride;
+            const long long ia = (seg0 + 2 * u) * stride, ib = ia + stride;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int n = p + P * i;
                 double a = 0.0, b = 0.0, w = 0.0;
                 if (act && n < nfft) {
                     w = __ldg(win + n);
-                    a = __ldg(xa + n);
-                    if (has_b) b = __ldg(xb + n);
+                    a = load_sample<FMT>(xv, ia + n);
+                    if (has_b) b = load_sample<FMT>(xv, ib + n);
                 }
                 z[i] = make_double2(w * a, w * b);
             }
@@ -137,14 +160,26 @@ __global__ void pwelch_fold_kernel(const double* __restrict__ partial, long long
 }
 
 // general path (any fftlen): dense windowed, zero-padded complex segments
-__global__ void pwelch_gather_kernel(const double* __restrict__ x, long long nfft, long long stride, long long seg0,
+__global__ void pwelch_gather_kernel(const void* __restrict__ x, int fmt, long long nfft, long long stride, long long seg0,
                                      long long nseg, long long fftlen, const double* __restrict__ win, cpx* __restrict__ buf) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= nseg * fftlen) return;
     long long c = t / fftlen, n = t - c * fftlen;
     double v = 0.0;
-    if (n < nfft) v = x[(seg0 + c) * stride + n] * win[n];
+    if (n < nfft) v = load_sample_rt(x, (seg0 + c) * stride + n, fmt) * win[n];
     buf[t] = make_double2(v, 0.0);
+}
+// window as a complex array (w[n], 0): the aux operand of the pass kernel's fused load multiply (STFT)
+__global__ void window_to_complex_kernel(const double* __restrict__ win, long long n, cpx* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(win[i], 0.0);
+}
+// dense spectra [nseg][fftlen] -> the first lp bins of each, [nseg][lp]
+__global__ void take_bins_kernel(const cpx* __restrict__ in, long long nseg, long long fftlen, long long lp, cpx* __restrict__ out) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= nseg * lp) return;
+    long long c = t / lp, j = t - c * lp;
+    out[t] = in[c * fftlen + j];
 }
 __global__ void pwelch_accum_kernel(const cpx* __restrict__ buf, long long nseg, long long fftlen, long long lp,
                                     double* __restrict__ raw) {
@@ -166,17 +201,23 @@ __global__ void pwelch_finalize_kernel(const double* __restrict__ raw, long long
     pxx[j] = d / norm;                         // :134-136
 }
 
+typedef void (*PwKernel)(const void*, long long, long long, long long, long long, const double*, double*, const cpx*);
 template <int LOG2L>
-static Status launch_fused(Device& d, const double* x, long long nfft, long long stride, long long lp, long long seg0,
+static Status launch_fused(Device& d, const void* x, int fmt, long long nfft, long long stride, long long lp, long long seg0,
                            long long nseg, const double* win, double* raw, cudaStream_t st) {
     using SH = PwShape<LOG2L>;
-    // the staged path needs every pair's sample range 16-byte aligned
+    // the staged path needs float64 samples and every pair's sample range 16-byte aligned
     // (pair u starts 2*u*stride doubles = 16*u*stride bytes after the first one)
-    const bool aligned = (reinterpret_cast<uintptr_t>(x + seg0 * stride) & 15) == 0;
-    auto kern = aligned ? pwelch_fused_kernel<LOG2L, true> : pwelch_fused_kernel<LOG2L, false>;
+    // and stride <= nfft (a pair's range of stride + nfft samples must fit the 2 L-sample buffer; noverlap < 0 leaves gaps)
+    const bool aligned = fmt == SMP_F64 && stride <= nfft && (reinterpret_cast<uintptr_t>((const double*)x + seg0 * stride) & 15) == 0;
+    PwKernel kern = aligned ? (PwKernel)pwelch_fused_kernel<LOG2L, true, SMP_F64>
+                  : fmt == SMP_F64 ? (PwKernel)pwelch_fused_kernel<LOG2L, false, SMP_F64>
+                  : fmt == SMP_F32 ? (PwKernel)pwelch_fused_kernel<LOG2L, false, SMP_F32>
+                  : fmt == SMP_S16 ? (PwKernel)pwelch_fused_kernel<LOG2L, false, SMP_S16>
+                                   : (PwKernel)pwelch_fused_kernel<LOG2L, false, SMP_U8>;
     const int threads = SH::T * SH::P, smem = SH::T * SH::LS * (int)sizeof(cpx);
-    static int bps[2][16] = {{0}};                       // per (variant, device): the opt-in below is a per-device attribute
-    int& blocks_per_sm = bps[aligned ? 1 : 0][d.dev & 15];
+    static int bps[5][16] = {{0}};                       // per (variant, device): the opt-in below is a per-device attribute
+    int& blocks_per_sm = bps[aligned ? 4 : fmt][d.dev & 15];
     if (!blocks_per_sm) {
         GD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int b = 0;
@@ -201,9 +242,9 @@ static Status launch_fused(Device& d, const double* x, long long nfft, long long
     return GD_OK;
 }
 
-Status pwelch_partial(Device& d, const double* x, long long nfft, long long stride, long long fftlen, long long lp,
+Status pwelch_partial(Device& d, const void* x, int fmt, long long nfft, long long stride, long long fftlen, long long lp,
                       long long seg0, long long nseg, const double* win, double* raw, cudaStream_t st) {
-    if (nfft < 1 || stride < 1 || fftlen < nfft || lp < 1 || lp > fftlen / 2 + 1 || nseg < 0) {
+    if (nfft < 1 || stride < 1 || fftlen < nfft || lp < 1 || lp > fftlen / 2 + 1 || nseg < 0 || fmt < SMP_F64 || fmt > SMP_U8) {
         set_error("pwelch: bad arguments");
         return GD_ERR_INVALID;
     }
@@ -215,14 +256,14 @@ Status pwelch_partial(Device& d, const double* x, long long nfft, long long stri
     const bool p2 = (fftlen & (fftlen - 1)) == 0;
     if (p2 && fftlen >= 32 && fftlen <= 4096) {
         switch (fftlen) {
-            case 32: return launch_fused<5>(d, x, nfft, stride, lp, seg0, nseg, win, raw, st);
-            case 64: return launch_fused<6>(d, x, nfft, stride, lp, seg0, nseg, win, raw, st);
-            case 128: return launch_fused<7>(d, x, nfft, stride, lp, seg0, nseg, win, raw, st);
-            case 256: return launch_fused<8>(d, x, nfft, stride, lp, seg0, nseg, win, raw, st);
-            case 512: return launch_fused<9>(d, x, nfft, stride, lp, seg0, nseg, win, raw, st);
-            case 1024: return launch_fused<10>(d, x, nfft, stride, lp, seg0, nseg, win, raw, st);
-            case 2048: return launch_fused<11>(d, x, nfft, stride, lp, seg0, nseg, win, raw, st);
-            case 4096: return launch_fused<12>(d, x, nfft, stride, lp, seg0, nseg, win, raw, st);
+            case 32: return launch_fused<5>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
+            case 64: return launch_fused<6>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
+            case 128: return launch_fused<7>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
+            case 256: return launch_fused<8>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
+            case 512: return launch_fused<9>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
+            case 1024: return launch_fused<10>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
+            case 2048: return launch_fused<11>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
+            case 4096: return launch_fused<12>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
         }
     }
     // general path: dense windowed segments -> batched transform (any length) -> per-bin sums
@@ -235,11 +276,54 @@ Status pwelch_partial(Device& d, const double* x, long long nfft, long long stri
     for (long long c0 = 0; c0 < nseg; c0 += chunk) {
         long long nc = nseg - c0 < chunk ? nseg - c0 : chunk;
         long long tot = nc * fftlen;
-        pwelch_gather_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, nfft, stride, seg0 + c0, nc, fftlen, win, buf);
+        pwelch_gather_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, fmt, nfft, stride, seg0 + c0, nc, fftlen, win, buf);
         g_launches++;
         GD_CUDA(cudaGetLastError());
         GD_TRY(fft1d(d, buf, fftlen, buf, fftlen, fftlen, nc, false, +1, st));
         pwelch_accum_kernel<<<(unsigned)((lp + 127) / 128), 128, 0, st>>>(buf, nc, fftlen, lp, raw);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+    }
+    return GD_OK;
+}
+
+// STFT / spectrogram: the Welch loop without the accumulate (spectral/pwelch.go:104-113): out[c][j] = FFT(win * segment c)[j],
+// j < lp, segments seg0 .. seg0 + nseg - 1 of stride `stride`. Power-of-two lengths are ONE fused launch per pass: the pass
+// kernel gathers the overlapping segments straight from the signal (rows `stride` samples apart), multiplies by the window,
+// zero-pads, transforms and stores only the first lp bins.
+Status stft(Device& d, const double* x, long long nfft, long long stride, long long fftlen, long long lp, long long seg0,
+            long long nseg, const double* win, cpx* out, cudaStream_t st) {
+    if (nfft < 1 || stride < 1 || fftlen < nfft || lp < 1 || lp > fftlen || nseg < 0) { set_error("stft: bad arguments"); return GD_ERR_INVALID; }
+    if (nseg == 0) return GD_OK;
+    GD_TRY(d.l2_release());
+    const bool p2 = (fftlen & (fftlen - 1)) == 0;
+    if (p2 && fftlen >= 2 && fftlen <= (1LL << 24)) {
+        cpx* wc;
+        GD_TRY(d.ensure_scratch(SCR_AUX, (size_t)nfft * sizeof(cpx), (void**)&wc));
+        window_to_complex_kernel<<<(unsigned)((nfft + 255) / 256), 256, 0, st>>>(win, nfft, wc);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+        FusedOps ops;
+        ops.ld_flags = LD_REAL | LD_PAD | LD_MULAUX;
+        ops.aux_in = wc; ops.n_valid_in = nfft;
+        ops.st_flags = ST_TRUNC; ops.n_valid_out = lp;
+        int lg = 0;
+        while ((1LL << lg) < fftlen) lg++;
+        return fft_pow2(d, x + seg0 * stride, stride, out, lp, lg, nseg, ops, st);
+    }
+    // any other length: dense windowed segments -> batched transform -> first lp bins
+    long long chunk = (long long)((64ull << 20) / ((size_t)fftlen * sizeof(cpx)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > nseg) chunk = nseg;
+    cpx* buf;
+    GD_TRY(d.ensure_scratch(SCR_PWELCH, (size_t)chunk * fftlen * sizeof(cpx), (void**)&buf));
+    for (long long c0 = 0; c0 < nseg; c0 += chunk) {
+        const long long nc = nseg - c0 < chunk ? nseg - c0 : chunk, tot = nc * fftlen;
+        pwelch_gather_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, SMP_F64, nfft, stride, seg0 + c0, nc, fftlen, win, buf);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+        GD_TRY(fft1d(d, buf, fftlen, buf, fftlen, fftlen, nc, false, +1, st));
+        take_bins_kernel<<<(unsigned)((nc * lp + 255) / 256), 256, 0, st>>>(buf, nc, fftlen, lp, out + c0 * lp);
         g_launches++;
         GD_CUDA(cudaGetLastError());
     }

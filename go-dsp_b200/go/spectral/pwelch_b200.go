@@ -56,7 +56,7 @@ func Pwelch(x []float64, Fs float64, o *PwelchOptions) (Pxx, freqs []float64) {
 	} else {
 		nsegs = (len(x)-nfft)/stride + 1
 	}
-	if nsegs < 1 || noverlap < 0 {
+	if nsegs < 1 { // Noverlap < 0 is valid: stride > nfft leaves gaps between segments, as spectral.Segment does
 		panic("runtime error: makeslice: len out of range")
 	}
 	fftlen := nfft

@@ -2,5 +2,6 @@
 window and dsputils with the Go names. Importing never touches the GPU; every transform call
 does, and fails loudly without one (there is no CPU fallback)."""
 from . import _capi, _host  # noqa: F401
-from . import dsputils, fft, spectral, window  # noqa: F401
+from . import dsputils, fft, spectral, wav, window  # noqa: F401
+from .device import DeviceBuffer  # noqa: F401
 from ._host import GoPanic  # noqa: F401

@@ -24,6 +24,16 @@ SIGNATURES = {
     "gd_fftn_c2c": (_int, [_vp, _vp, C.POINTER(_i64), _int, _int]),
     "gd_plan_warm": (_int, [_i64]), "gd_bluestein_padded_len": (_i64, [_i64]),
     "gd_pwelch_f64": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, C.c_double, _vp]),
+    "gd_pwelch_samples": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _vp, C.c_double, _vp]),
+    "gd_pwelch_stream_begin": (_int, [C.POINTER(_vp), _int, _i64, _i64, _i64, _i64, _vp]),
+    "gd_pwelch_stream_push": (_int, [_vp, _vp, _i64]),
+    "gd_pwelch_stream_end": (_int, [_vp, C.c_double, _vp, C.POINTER(_i64)]),
+    "gd_stft_f64": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "gd_fft_segments_c2c": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "gd_convolve_linear_c2c": (_int, [_vp, _i64, _vp, _i64, _vp]),
+    "gd_pwelch_partial_samples_dev": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "gd_stft_f64_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "gd_convolve_linear_c2c_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "gd_pinned_alloc": (_vp, [_sz]), "gd_pinned_free": (None, [_vp]),
     "gd_dev_alloc": (_int, [C.POINTER(_vp), _sz]), "gd_dev_free": (_int, [_vp]),
     "gd_memcpy_h2d": (_int, [_vp, _vp, _sz]), "gd_memcpy_d2h": (_int, [_vp, _vp, _sz]),

@@ -75,6 +75,32 @@ def FFTBatch(x, n, direction=1):
     return out
 
 
+def ConvolveLinear(x, h):
+    """Linear convolution, len(x) + len(h) - 1 outputs, by overlap-save on the circular Convolve (fft/fft.go:55-69); what a
+    go-dsp user computes as Convolve(ZeroPad(x, m), ZeroPad(h, m))[:n], n = len(x) + len(h) - 1, m = NextPowerOf2(n)."""
+    from . import _capi
+    x, h = _c(x).reshape(-1), _c(h).reshape(-1)
+    if x.shape[0] == 0 or h.shape[0] == 0:
+        return np.empty(0, np.complex128)
+    out = np.empty(x.shape[0] + h.shape[0] - 1, np.complex128)
+    _capi.check(_capi.lib().gd_convolve_linear_c2c(x.ctypes.data, x.shape[0], h.ctypes.data, h.shape[0], out.ctypes.data))
+    return out
+
+
+def FFTSegments(x, segs, noverlap):
+    """fft.FFT(dsputils.ZeroPad2(s)) for every slice s of dsputils.Segment(x, segs, noverlap) (dsputils/dsputils.go:72-75,
+    89-115), one batched launch; the slices are described to the GPU (offset, length), never copied."""
+    from . import _capi, dsputils
+    x = _c(x).reshape(-1)
+    sl = dsputils.Segment(x, segs, noverlap)
+    length = len(sl[0])
+    step = (sl[1].ctypes.data - sl[0].ctypes.data) // 16 if segs > 1 else max(length, 1)
+    fftlen = dsputils.NextPowerOf2(length)
+    out = np.empty((segs, fftlen), np.complex128)
+    _capi.check(_capi.lib().gd_fft_segments_c2c(x.ctypes.data, x.shape[0], length, max(step, 1), segs, fftlen, out.ctypes.data))
+    return out
+
+
 def SetWorkerPoolSize(n): _host.lib().gdh_set_worker_pool_size(int(n))          # fft/fft.go:95 (no effect on the GPU)
 def EnsureRadix2Factors(n): _host.check(_host.lib().gdh_ensure_radix2_factors(int(n)))   # fft/radix2.go:35
 def reverseBits(v, s): return int(_host.lib().gdh_reverse_bits(int(v), int(s)))  # fft/radix2.go:184

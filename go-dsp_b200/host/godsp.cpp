@@ -315,7 +315,8 @@ std::pair<rvec, rvec> Pwelch(const rvec& xin, double Fs, const PwelchOptions* o)
     if ((int64_t)xin.size() < nfft) { padded = dsputils::ZeroPadF(xin, nfft); x = &padded; }
     const int64_t lp = pad / 2 + 1;
     const int64_t nsegs = SegmentCount((int64_t)x->size(), nfft, noverlap);
-    if (nsegs < 1 || noverlap < 0 || noverlap >= nfft) throw Panic("runtime error: makeslice: len out of range");
+    // Noverlap < 0 is valid in the reference: stride = size - noverlap > size leaves gaps between the segments
+    if (nsegs < 1 || noverlap >= nfft) throw Panic("runtime error: makeslice: len out of range");
     const int64_t fftlen = pad > nfft ? pad : nfft;          // len(ZeroPadF(segment, pad))
     rvec win = wf(fftlen);                                    // window.Apply(x, wf) -> wf(len(x))
     if ((int64_t)win.size() < fftlen) throw Panic("runtime error: index out of range");

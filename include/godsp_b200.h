@@ -92,6 +92,34 @@ GD_API int64_t gd_bluestein_padded_len(int64_t n);
 GD_API int gd_pwelch_f64(const double* x, int64_t nx, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
                   int64_t nsegs, const double* win, double norm, double* pxx);
 
+
+/* ---- the callers and data formats either side of the path ---------------- */
+/* Sample formats: float64, or the formats wav.ReadSamples yields (wav/wav.go:113-136), decoded on the device exactly as
+ * wav.ReadFloats does (wav/wav.go:138-161, float32 arithmetic: uint8 -> v/255, int16 -> (v+32768)/65535, float32 as is)
+ * and widened to float64. The decode is part of the Pwelch kernel's segment load, so the signal crosses PCIe at its
+ * on-disk width (1, 2 or 4 bytes per sample instead of 8). */
+enum { GD_SAMPLE_F64 = 0, GD_SAMPLE_F32 = 1, GD_SAMPLE_S16 = 2, GD_SAMPLE_U8 = 3 };
+/* gd_pwelch_f64 for any sample format. */
+GD_API int gd_pwelch_samples(const void* x, int sample_fmt, int64_t nx, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
+                      int64_t nsegs, const double* win, double norm, double* pxx);
+/* Streaming spectral.Pwelch: the signal arrives in chunks of any size (a wav file read block by block); segments that
+ * straddle two chunks are handled by the library. begin -> push* -> end; end writes Pxx (lp values, same scaling as
+ * gd_pwelch_f64 with the final segment count) and the number of segments, and frees the handle. Pass pxx = NULL to abandon. */
+GD_API int gd_pwelch_stream_begin(void** handle, int sample_fmt, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp, const double* win);
+GD_API int gd_pwelch_stream_push(void* handle, const void* samples, int64_t n);
+GD_API int gd_pwelch_stream_end(void* handle, double norm, double* pxx, int64_t* nsegs_out);
+/* STFT / spectrogram: the segment loop of spectral.Pwelch without the accumulate (spectral/pwelch.go:104-113):
+ * out[c*lp + j] = FFT(win * segment c, zero-padded to fftlen)[j], j < lp (lp <= fftlen), c < nsegs; complex128. */
+GD_API int gd_stft_f64(const double* x, int64_t nx, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp, int64_t nsegs,
+                const double* win, double* out);
+/* fft.FFT of every slice dsputils.Segment returns (dsputils/dsputils.go:89-115: segs slices of seg_len elements, `step`
+ * apart, aliasing x), each zero-padded to fftlen as dsputils.ZeroPad2 does (dsputils.go:72-75; fftlen a power of two
+ * >= seg_len). The slices are described, not copied: the transform reads them in place. out: segs x fftlen complex128. */
+GD_API int gd_fft_segments_c2c(const double* x, int64_t nx, int64_t seg_len, int64_t step, int64_t segs, int64_t fftlen, double* out);
+/* Linear (non-circular) convolution, nx + nh - 1 outputs, by overlap-save on top of fft.Convolve's circular product
+ * (fft/fft.go:55-69); equal to Convolve of both operands zero-padded (dsputils.ZeroPad) to a power of two >= nx + nh - 1. */
+GD_API int gd_convolve_linear_c2c(const double* x, int64_t nx, const double* h, int64_t nh, double* out);
+
 /* ---- staging memory for the shim -------------------------------------------------------- */
 GD_API void* gd_pinned_alloc(size_t bytes);
 GD_API void gd_pinned_free(void* p);
@@ -135,6 +163,11 @@ GD_API int gd_ipc_close(void* p);
 /* raw[j] = sum over segments seg0..seg0+nseg-1 of |FFT(win * segment)[j]|^2, j < lp (one GPU's share) */
 GD_API int gd_pwelch_partial_dev(const double* x_dev, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
                           int64_t seg0, int64_t nseg, const double* win_dev, double* raw_dev, void* stream);
+GD_API int gd_pwelch_partial_samples_dev(const void* x_dev, int sample_fmt, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
+                                  int64_t seg0, int64_t nseg, const double* win_dev, double* raw_dev, void* stream);
+GD_API int gd_stft_f64_dev(const double* x_dev, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp, int64_t seg0, int64_t nseg,
+                    const double* win_dev, double* out_dev, void* stream);
+GD_API int gd_convolve_linear_c2c_dev(const double* x_dev, int64_t nx, const double* h_dev, int64_t nh, double* out_dev, void* stream);
 /* pxx[j] = raw[j] / nsegs (x2 for 0 < j < lp-1) / norm */
 GD_API int gd_pwelch_finalize_dev(const double* raw_dev, int64_t lp, int64_t nsegs, double norm, double* pxx_dev, void* stream);
 /* number of kernels this library has launched on the calling thread's device since gd_init */

@@ -48,6 +48,10 @@ def lib():
             "gdo_segment_count": (i64, [i64, i64, i64]), "gdo_segment": (None, [_dp, i64, i64, i64, _dp]),
             "gdo_pwelch": (i64, [_dp, i64, dbl, i64, i64, i64, _dp, _dp, ci, _dp, _dp, ci]),
             "gdo_fft_batch": (None, [_dp, _dp, i64, i64, ci]),
+            "gdo_stft": (i64, [_dp, i64, i64, i64, i64, i64, _dp, _dp]),
+            "gdo_dsputils_segment": (ci, [i64, i64, dbl, C.POINTER(i64), C.POINTER(i64)]),
+            "gdo_wav_new": (ci, [C.c_char_p, i64, C.POINTER(i64)]),
+            "gdo_wav_read_floats": (ci, [C.c_char_p, ci, i64, C.POINTER(C.c_float)]),
             "gdo_fill_splitmix": (None, [_dp, i64, u64, u64]),
             "gdo_max_threads": (ci, []),
         }
@@ -179,3 +183,61 @@ def fill_splitmix(n, seed, offset=0):
 def splitmix_complex(n, seed, offset=0):
     """complex element i uses counters 2i (re), 2i+1 (im)."""
     return fill_splitmix(2 * n, seed, 2 * offset).view(np.complex128)
+
+
+def stft(x, nfft, noverlap=0, pad=0, window_fn="hann"):
+    """The segment loop of spectral.Pwelch without the accumulate (spectral/pwelch.go:104-113): [nsegs][pad/2+1] complex."""
+    x = _r(x)
+    pad = pad or nfft
+    fftlen = max(pad, nfft)
+    lp = pad // 2 + 1
+    wf = (lambda L: window(window_fn or "hann", L)) if (window_fn is None or isinstance(window_fn, str)) else window_fn
+    wa = _r(wf(fftlen))
+    n = segment_count(x.shape[0], nfft, noverlap)
+    out = np.empty((n, lp), np.complex128)
+    got = lib().gdo_stft(_p(x), x.shape[0], nfft, noverlap, fftlen, lp, _p(wa), _p(out))
+    assert got == n
+    return out
+
+
+def dsputils_segment(lx, segs, noverlap):
+    """(length, step) of dsputils.Segment's slices (dsputils/dsputils.go:89-115); raises like the reference panics."""
+    ln, st = C.c_int64(0), C.c_int64(0)
+    if lib().gdo_dsputils_segment(lx, segs, float(noverlap), C.byref(ln), C.byref(st)) != 0:
+        raise ValueError("too many segments")
+    return ln.value, st.value
+
+
+WAV_ERRORS = {1: "unexpected EOF", 2: "wav: missing RIFF", 3: "wav: missing WAVE", 4: "wav: bad fmt size",
+              5: "wav: unknown audio format", 6: "wav: unexpected fmt chunk"}
+
+
+def wav_new(data):
+    """wav.New (wav/wav.go:59-110) on the bytes of a file: dict of header fields, Samples, Duration (ns), data offset/size."""
+    hdr = (C.c_int64 * 10)()
+    rc = lib().gdo_wav_new(bytes(data), len(data), hdr)
+    if rc:
+        raise ValueError(WAV_ERRORS[rc])
+    keys = ("AudioFormat", "NumChannels", "SampleRate", "ByteRate", "BlockAlign", "BitsPerSample", "Samples", "Duration", "data_offset", "data_size")
+    return dict(zip(keys, [int(v) for v in hdr]))
+
+
+def wav_read_floats(raw, fmt, n):
+    """wav.ReadFloats (wav/wav.go:138-161) on raw little-endian sample bytes; fmt: 1 float32, 2 int16, 3 uint8."""
+    out = np.empty(n, np.float32)
+    if lib().gdo_wav_read_floats(bytes(raw), fmt, n, out.ctypes.data_as(C.POINTER(C.c_float))) != 0:
+        raise ValueError("wav: unknown type")
+    return out
+
+
+def convolve_linear(x, h):
+    """Linear convolution the way a go-dsp user gets it: fft.Convolve (fft/fft.go:55-69) of both operands zero-padded with
+    dsputils.ZeroPad to the next power of two >= len(x) + len(h) - 1 (dsputils.NextPowerOf2, as ZeroPad2 pads), truncated.
+    (Padding to exactly len(x) + len(h) - 1 would route a non power of two through Bluestein, whose chirp phase is only good
+    to ~N*eps rad, fft/bluestein.go:53 -- 3e-11 at N = 10^5.)"""
+    x, h = _c(x), _c(h)
+    n = x.shape[0] + h.shape[0] - 1
+    m = next_pow2(n)
+    xp, hp = np.zeros(m, np.complex128), np.zeros(m, np.complex128)
+    xp[: x.shape[0]], hp[: h.shape[0]] = x, h
+    return convolve(xp, hp)[:n]

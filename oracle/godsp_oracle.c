@@ -436,6 +436,102 @@ int64_t gdo_pwelch(const double *x, int64_t lx, double Fs, int64_t nfft, int64_t
     return lp;
 }
 
+/* ------------------------------------------------------------------ callers / formats either side of the path */
+
+/* spectral/pwelch.go:104-113 without the accumulate (STFT / spectrogram): for every segment of
+ * spectral.Segment(x, nfft, noverlap): ZeroPadF to fftlen = max(pad, nfft), window.Apply, FFTReal; the
+ * first lp bins of each spectrum go to out[s*lp + j]. Returns the segment count. */
+int64_t gdo_stft(const double *x, int64_t lx, int64_t nfft, int64_t noverlap, int64_t fftlen, int64_t lp,
+                 const double *win_apply, double *out) {
+    int64_t nsegs = gdo_segment_count(lx, nfft, noverlap), stride = nfft - noverlap;
+    if (gdo_is_pow2(fftlen) && fftlen >= 4) ensure_factors(fftlen);
+    c128 *buf = (c128 *)malloc((size_t)fftlen * sizeof(c128));
+    c128 *spec = (c128 *)malloc((size_t)fftlen * sizeof(c128));
+    for (int64_t s = 0; s < nsegs; s++) {
+        const double *seg = x + s * stride;
+        for (int64_t i = 0; i < fftlen; i++) {
+            double v = i < nfft ? seg[i] : 0.0;
+            buf[i].re = v * win_apply[i]; buf[i].im = 0;
+        }
+        fft_any(buf, spec, fftlen);
+        for (int64_t j = 0; j < lp; j++) { out[2 * (s * lp + j)] = spec[j].re; out[2 * (s * lp + j) + 1] = spec[j].im; }
+    }
+    free(buf); free(spec);
+    return nsegs;
+}
+
+/* dsputils/dsputils.go:89-115  Segment: the (length, step) of the segs aliasing slices; returns 0, or -1 for the
+ * reference's panic("too many segments"). */
+int gdo_dsputils_segment(int64_t lx, int64_t segs, double noverlap, int64_t *length_out, int64_t *step_out) {
+    int64_t overlap = 0, length, step = 0, tot;
+    for (length = lx; length > 0; length--) {                        /* :94-101 */
+        overlap = (int64_t)((double)length * noverlap);
+        tot = segs * (length - overlap) + overlap;
+        if (tot <= lx) { step = length - overlap; break; }
+    }
+    if (length == 0) return -1;                                      /* :103-105 */
+    *length_out = length; *step_out = step;
+    return 0;
+}
+
+/* wav/wav.go:59-110  New: RIFF/WAVE header walk. hdr[0..5] = AudioFormat, NumChannels, SampleRate, ByteRate,
+ * BlockAlign, BitsPerSample; hdr[6] = Samples, hdr[7] = Duration in ns, hdr[8] = offset of the data bytes,
+ * hdr[9] = data chunk size. Returns 0, or: 1 short read, 2 missing RIFF, 3 missing WAVE, 4 bad fmt size,
+ * 5 unknown audio format, 6 data chunk before fmt. */
+int gdo_wav_new(const unsigned char *b, int64_t n, int64_t *hdr) {
+    if (n < 12) return 1;                                            /* :62-64 */
+    if (memcmp(b, "RIFF", 4) != 0) return 2;                         /* :65-67 */
+    if (memcmp(b + 8, "WAVE", 4) != 0) return 3;                     /* :68-70 */
+    int64_t pos = 12;
+    int has_fmt = 0;
+    for (;;) {
+        if (pos + 8 > n) return 1;                                   /* :73-75 */
+        uint32_t sz = (uint32_t)b[pos + 4] | ((uint32_t)b[pos + 5] << 8) | ((uint32_t)b[pos + 6] << 16) | ((uint32_t)b[pos + 7] << 24);
+        const unsigned char *typ = b + pos;
+        pos += 8;
+        if (memcmp(typ, "fmt ", 4) == 0) {                           /* :78-96 */
+            if (sz < 16) return 4;
+            if (pos + (int64_t)sz > n) return 1;
+            const unsigned char *f = b + pos;
+            hdr[0] = f[0] | (f[1] << 8);
+            hdr[1] = f[2] | (f[3] << 8);
+            hdr[2] = (int64_t)((uint32_t)f[4] | ((uint32_t)f[5] << 8) | ((uint32_t)f[6] << 16) | ((uint32_t)f[7] << 24));
+            hdr[3] = (int64_t)((uint32_t)f[8] | ((uint32_t)f[9] << 8) | ((uint32_t)f[10] << 16) | ((uint32_t)f[11] << 24));
+            hdr[4] = f[12] | (f[13] << 8);
+            hdr[5] = f[14] | (f[15] << 8);
+            if (hdr[0] != 1 && hdr[0] != 3) return 5;
+            has_fmt = 1;
+            pos += sz;
+        } else if (memcmp(typ, "data", 4) == 0) {                    /* :97-104 */
+            if (!has_fmt) return 6;
+            hdr[6] = (int64_t)sz / hdr[5] * 8;                       /* int(sz) / int(BitsPerSample) * 8, left to right */
+            hdr[7] = hdr[6] * 1000000000LL / hdr[2] / hdr[1];        /* Duration(Samples) * Second / SampleRate / NumChannels */
+            hdr[8] = pos; hdr[9] = sz;
+            return 0;
+        } else {
+            pos += sz;                                               /* :105-106 io.CopyN(ioutil.Discard, r, sz) */
+        }
+    }
+}
+
+/* wav/wav.go:138-161  ReadFloats on n raw little-endian samples: fmt 1 = float32 as is, 2 = int16 ->
+ * (float32(v) - MinInt16) / (MaxInt16 - MinInt16), 3 = uint8 -> float32(v) / MaxUint8, all in float32. */
+int gdo_wav_read_floats(const unsigned char *data, int fmt, int64_t n, float *out) {
+    for (int64_t i = 0; i < n; i++) {
+        if (fmt == 3) {
+            volatile float f = (float)data[i];
+            out[i] = f / 255.0f;                                     /* :145-148 */
+        } else if (fmt == 2) {
+            int16_t v = (int16_t)((uint16_t)data[2 * i] | ((uint16_t)data[2 * i + 1] << 8));
+            volatile float f = (float)v - (-32768.0f);
+            out[i] = f / (32767.0f - (-32768.0f));                   /* :150-153 */
+        } else if (fmt == 1) {
+            memcpy(out + i, data + 4 * i, 4);                        /* :154-155 */
+        } else return -1;
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ bench helpers */
 
 /* Independent transforms of one batch, one per OpenMP thread at a time (bench

@@ -7,10 +7,13 @@ It parses the Go table literals (data only -- no reference code is copied) and
 writes tests/golden/reference_vectors.json, recording the file:line range each
 table came from.  Complex values are stored as [re, im] pairs.
 """
+import ast
 import json
 import math
+import operator
 import os
 import re
+import shutil
 import sys
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
@@ -34,9 +37,30 @@ def go_block(path, var):
     body = re.sub(r"(\[\])+\s*\w+\s*\{", "{", body)        # []float64{ / [][]complex128{ / []fftTest{
     body = re.sub(r"&\w+\{\}", "None", body)               # &PwelchOptions{}
     body = body.replace("{", "[").replace("}", "]")
-    env = {"complex": complex, "sqrt2_2": math.sqrt(2) / 2, "None": None}
-    val = eval(body, {"__builtins__": {}}, env)
-    return val, "%s:%d-%d" % (path, start + 1, end + 1)
+    return literal(ast.parse(body.strip(), mode="eval").body), "%s:%d-%d" % (path, start + 1, end + 1)
+
+
+NAMES = {"sqrt2_2": math.sqrt(2) / 2, "None": None}
+BINOPS = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: operator.truediv}
+
+
+def literal(node):
+    """The reference tree is untrusted text: only numbers, lists, +-*/ of those, complex(a, b) and two known names are
+    evaluated (no eval, no attribute access, no other calls)."""
+    if isinstance(node, ast.Constant) and (node.value is None or isinstance(node.value, (int, float))):
+        return node.value
+    if isinstance(node, (ast.List, ast.Tuple)):
+        return [literal(e) for e in node.elts]
+    if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+        v = literal(node.operand)
+        return -v if isinstance(node.op, ast.USub) else v
+    if isinstance(node, ast.BinOp) and type(node.op) in BINOPS:
+        return BINOPS[type(node.op)](literal(node.left), literal(node.right))
+    if isinstance(node, ast.Name) and node.id in NAMES:
+        return NAMES[node.id]
+    if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id == "complex" and len(node.args) == 2 and not node.keywords:
+        return complex(literal(node.args[0]), literal(node.args[1]))
+    raise ValueError("unsupported construct in a reference table: %s" % ast.dump(node)[:80])
 
 
 def enc(v):
@@ -49,6 +73,28 @@ def enc(v):
 
 def cplx_list(v):
     return [[complex(e).real, complex(e).imag] for e in v]
+
+
+def wav_golden():
+    """wav/wav_test.go:66-98 TestWav: the header fields, Samples and Duration wav.New must report for the two fixtures.
+    The fixtures themselves are test data, copied next to this script: small.wav whole (84 KB) and float.wav cut after
+    its first 16384 samples (the header still announces the full data size, which is what the test checks)."""
+    src = open(os.path.join(REF, "wav/wav_test.go")).read()
+    cases = {}
+    for name in ("small.wav", "float.wav"):
+        blk = src[src.index('"%s": {' % name):]
+        blk = blk[: blk.index("typ:")]
+        f = {k: literal(ast.parse(re.search(r"%s:\s*([0-9 /*]+)," % k, blk).group(1).strip(), mode="eval").body)
+             for k in ("AudioFormat", "NumChannels", "SampleRate", "ByteRate", "BlockAlign", "BitsPerSample", "Samples", "Duration")}
+        f["Samples"] = int(f["Samples"])
+        cases[name] = f
+    here = os.path.dirname(OUT)
+    shutil.copyfile(os.path.join(REF, "wav/small.wav"), os.path.join(here, "small.wav"))
+    with open(os.path.join(REF, "wav/float.wav"), "rb") as fsrc, open(os.path.join(here, "float_head.wav"), "wb") as fdst:
+        fdst.write(fsrc.read(44 + 4 * 16384))
+    os.chmod(os.path.join(here, "small.wav"), 0o644)
+    return {"source": "wav/wav_test.go:66-98", "files": {"small.wav": "small.wav", "float.wav": "float_head.wav"}, "cases": cases,
+            "note": "decoded sample values are not pinned by any reference test: ReadFloats (wav/wav.go:138-161) is pinned by its source lines only"}
 
 
 def main():
@@ -86,6 +132,7 @@ def main():
         "dim_cases": [{"idx": [1, 0, -1], "out": [3, 4, 5, 6]}, {"idx": [0, -1, 2], "out": [3, 7, 1]},
                       {"idx": [-1, 1, 3], "out": [8, 0]}],
         "setdim": {"idx": [1, -1, 3], "values": [10, 11, 12]}}
+    out["wav"] = wav_golden()
     with open(OUT, "w") as f:
         json.dump(enc(out), f, indent=1)
     print("wrote", OUT, {k: len(v["cases"]) for k, v in out.items() if isinstance(v, dict) and "cases" in v})

@@ -123,6 +123,19 @@ def test_real_roundtrips(gd):                    # C2: IFFT(FFTReal(x)) ~ x and 
         assert rel_l2(godsp.fft.IFFTReal(r), oracle.ifft_real(r)) <= TOL
 
 
+def test_above_2p24_single_gpu(gd):              # the reference has no length limit (fft/fft.go:72-87): outer four-step above 2^24
+    godsp, capi, L = gd
+    n = 1 << 25
+    x = oracle.splitmix_complex(n, 1)
+    X = godsp.fft.FFT(x)
+    assert rel_l2(X, oracle.fft(x)) <= TOL
+    assert rel_l2(godsp.fft.IFFT(X), x) <= TOL
+    # a Bluestein length whose padded size exceeds 2^24 is refused loudly (documented limit), never computed on the CPU
+    y = np.zeros(9000001, np.complex128)
+    with pytest.raises(godsp.GoPanic, match="2\\^24"):
+        godsp.fft.FFT(y)
+
+
 def test_bluestein_padding_lengths(gd):
     L = gd[2]
     for n in (3, 5, 1000, 65537, 1000003):

@@ -3,6 +3,7 @@ reference's own tests hold for the FFT / Pwelch path (tests/golden/reference_vec
 extracted from go-dsp's *_test.go files), with the reference's own tolerance
 (dsputils.Float64Equal, 1e-8 abs-or-rel).  CPU only."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -138,3 +139,62 @@ def test_splitmix_matches_numpy():
         z ^= z >> np.uint64(31)
     want = (z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53 * 2 - 1
     assert np.array_equal(oracle.fill_splitmix(n, seed), want)
+
+
+# ----------------------------------------------------------------- wav ingest, dsputils.Segment
+def test_wav_header_golden(golden):              # wav/wav_test.go:66-98 TestWav, on the copied fixtures
+    g = golden["wav"]
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name, fn in g["files"].items():
+        data = open(os.path.join(here, fn), "rb").read()
+        h = oracle.wav_new(data)
+        for k, v in g["cases"][name].items():
+            assert h[k] == v, (name, k, h[k], v)
+        assert h["data_offset"] == 44
+
+
+def test_wav_header_errors():                    # wav/wav.go:62-70,80-82,93,99: the reference's error returns
+    import pytest
+    riff = b"RIFF\0\0\0\0WAVE"
+    for data, msg in ((b"RIF", "EOF"), (b"XXXX\0\0\0\0WAVE", "missing RIFF"), (b"RIFF\0\0\0\0WAVX", "missing WAVE"),
+                      (riff + b"fmt \x08\0\0\0" + b"\0" * 8, "bad fmt size"),
+                      (riff + b"fmt \x10\0\0\0" + b"\x07\0" + b"\0" * 14, "unknown audio format"),
+                      (riff + b"data\x04\0\0\0\0\0\0\0", "unexpected fmt chunk"), (riff + b"JUNK\x02\0\0\0ab", "EOF")):
+        with pytest.raises(ValueError, match=msg):
+            oracle.wav_new(data)
+
+
+def test_wav_read_floats_exact():                # wav/wav.go:138-161: float32 arithmetic, every int16 / uint8 value
+    i16 = np.arange(-32768, 32768, dtype=np.int16)
+    got = oracle.wav_read_floats(i16.astype("<i2").tobytes(), 2, i16.size)
+    want = (i16.astype(np.float32) - np.float32(-32768)) / np.float32(65535)
+    assert np.array_equal(got, want) and got[0] == 0.0 and got[-1] == 1.0
+    u8 = np.arange(256, dtype=np.uint8)
+    assert np.array_equal(oracle.wav_read_floats(u8.tobytes(), 3, 256), u8.astype(np.float32) / np.float32(255))
+    f = np.array([0.5, -1.25, 3e-8], np.float32)
+    assert np.array_equal(oracle.wav_read_floats(f.tobytes(), 1, 3), f)
+
+
+def test_dsputils_segment_golden(golden):        # dsputils/dsputils_test.go:28-57
+    g = golden["dsputils_segment"]
+    for c in g["cases"]:
+        length, step = oracle.dsputils_segment(g["n"], c["segs"], c["noverlap"])
+        assert [[i * step, i * step + length] for i in range(c["segs"])] == c["slices"]
+    import pytest
+    with pytest.raises(ValueError):
+        oracle.dsputils_segment(4, 9, 0.0)       # dsputils.go:103-105 panic("too many segments")
+
+
+def test_stft_is_pwelch_without_the_sum():       # spectral/pwelch.go:104-122: Pxx from the per-segment spectra
+    x = oracle.fill_splitmix(5000, 9)
+    S = oracle.stft(x, 256, 128, pad=512, window_fn="hamming")
+    p, _ = oracle.pwelch(x, 2.0, nfft=256, pad=512, noverlap=128, window_fn="hamming")
+    d = (S.real ** 2 + S.imag ** 2) / S.shape[0]
+    d[:, 1:-1] *= 2.0
+    norm = float(np.sum(oracle.window("hamming", 256) ** 2)) * 2.0
+    assert np.allclose(d.sum(0) / norm, p, rtol=1e-13, atol=0)
+
+
+def test_convolve_linear_matches_direct():
+    x, h = oracle.splitmix_complex(300, 1), oracle.splitmix_complex(17, 2)
+    assert np.allclose(oracle.convolve_linear(x, h), np.convolve(x, h), rtol=0, atol=1e-12)
