@@ -284,8 +284,9 @@ int gd_set_option(const char* key, int64_t value) {
     GD_ENTER();
     if (!strcmp(key, "pass_scratch_mb")) { if (value < 1) return (int)invalid_arg("pass_scratch_mb < 1"); d.pass_scratch_budget = (size_t)value << 20; }
     else if (!strcmp(key, "l2_block_mb")) { if (value < 1) return (int)invalid_arg("l2_block_mb < 1"); d.l2_block_budget = (size_t)value << 20; }
-    else if (!strcmp(key, "two_stream_chunks")) d.two_stream_chunks = value != 0;
+    else if (!strcmp(key, "chunk_streams")) { if (value < 1 || value > 4) return (int)invalid_arg("chunk_streams out of range"); d.chunk_streams = (int)value; }
     else if (!strcmp(key, "l2_block_window")) d.l2_block_window = value != 0;
+    else if (!strcmp(key, "pwelch_bulk")) d.pwelch_bulk = value != 0;
     else if (!strcmp(key, "wide_tiles")) d.wide_tiles = value != 0;
     else if (!strcmp(key, "fused")) d.use_fused = value != 0;
     else if (!strcmp(key, "debug_alias")) d.debug_alias = value != 0;

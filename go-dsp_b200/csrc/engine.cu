@@ -76,9 +76,11 @@ Status Device::init(int device) {
     GD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     GD_CUDA(cudaStreamCreateWithFlags(&stream_in, cudaStreamNonBlocking));
     GD_CUDA(cudaStreamCreateWithFlags(&stream_out, cudaStreamNonBlocking));
-    GD_CUDA(cudaStreamCreateWithFlags(&stream_aux, cudaStreamNonBlocking));
+    for (int i = 0; i < AUX_STREAMS; i++) {
+        GD_CUDA(cudaStreamCreateWithFlags(&stream_aux[i], cudaStreamNonBlocking));
+        GD_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+    }
     GD_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    GD_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     for (int k = 5; k <= 12; k++) {
         std::vector<cpx> h;
         host_twiddles(h, 1LL << k, 1, 1LL << k);
@@ -113,10 +115,11 @@ void Device::destroy() {
     for (auto& kv : blue) { cudaFree(kv.second.chirp_inv); cudaFree(kv.second.bhat); }
     blue.clear();
     for (int i = 0; i < SCR_NSLOTS; i++) { if (scratch[i]) cudaFree(scratch[i]); scratch[i] = nullptr; scratch_bytes[i] = 0; }
-    cudaStreamDestroy(stream); cudaStreamDestroy(stream_in); cudaStreamDestroy(stream_out); cudaStreamDestroy(stream_aux);
-    cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
-    stream = stream_in = stream_out = stream_aux = nullptr;
-    ev_fork = ev_join = nullptr;
+    cudaStreamDestroy(stream); cudaStreamDestroy(stream_in); cudaStreamDestroy(stream_out);
+    for (int i = 0; i < AUX_STREAMS; i++) { cudaStreamDestroy(stream_aux[i]); cudaEventDestroy(ev_join[i]); stream_aux[i] = nullptr; ev_join[i] = nullptr; }
+    cudaEventDestroy(ev_fork);
+    stream = stream_in = stream_out = nullptr;
+    ev_fork = nullptr;
     ready = false;
 }
 
@@ -189,15 +192,23 @@ static PassParams base_params(Device& d, int log2l) {
     return p;
 }
 
-// Alternate independent chunks of one call between the caller's stream and the device's auxiliary stream.
+// Spread the independent chunks of one call over `ways` streams: the caller's and the device's auxiliary ones. Each way
+// has its own scratch block; short launches of different chunks fill each other's ramps and tails.
 struct ForkJoin {
     Device& d;
     cudaStream_t st;
-    bool on, window = false;
-    ForkJoin(Device& dev, cudaStream_t s, bool enable) : d(dev), st(s), on(enable && dev.stream_aux && s != dev.stream_aux) {
-        if (on) { cudaEventRecord(d.ev_fork, st); cudaStreamWaitEvent(d.stream_aux, d.ev_fork, 0); }
+    int ways;
+    bool window = false;
+    ForkJoin(Device& dev, cudaStream_t s, int want) : d(dev), st(s), ways(want < 1 ? 1 : want) {
+        if (ways > 1 + Device::AUX_STREAMS) ways = 1 + Device::AUX_STREAMS;
+        for (int i = 0; i < Device::AUX_STREAMS; i++) if (s == d.stream_aux[i]) ways = 1;
+        if (ways > 1) {
+            cudaEventRecord(d.ev_fork, st);
+            for (int i = 0; i + 1 < ways; i++) cudaStreamWaitEvent(d.stream_aux[i], d.ev_fork, 0);
+        }
     }
-    cudaStream_t stream(long long i) const { return on && (i & 1) ? d.stream_aux : st; }
+    int way(long long i) const { return (int)(i % ways); }
+    cudaStream_t stream(long long i) const { const int w = way(i); return w == 0 ? st : d.stream_aux[w - 1]; }
     // keep the inter-pass blocks in L2: persisting access-policy window over the scratch on the streams of this call
     void persist(void* base, size_t bytes) {
         if (!d.l2_block_window || !d.use_l2_window || d.l2_persist_max == 0 || d.l2_window_max == 0) return;
@@ -222,11 +233,11 @@ struct ForkJoin {
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         }
         cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-        if (on) cudaStreamSetAttribute(d.stream_aux, cudaStreamAttributeAccessPolicyWindow, &attr);
+        for (int i = 0; i + 1 < ways; i++) cudaStreamSetAttribute(d.stream_aux[i], cudaStreamAttributeAccessPolicyWindow, &attr);
     }
     ~ForkJoin() {
         if (window) { set(nullptr, 0, 0.0); d.l2_hold = false; d.l2_dirty = true; }
-        if (on) { cudaEventRecord(d.ev_join, d.stream_aux); cudaStreamWaitEvent(st, d.ev_join, 0); }
+        for (int i = 0; i + 1 < ways; i++) { cudaEventRecord(d.ev_join[i], d.stream_aux[i]); cudaStreamWaitEvent(st, d.ev_join[i], 0); }
     }
 };
 
@@ -347,23 +358,23 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
     TwiddleTable tw;
     GD_TRY(d.twiddles(log2n, &tw));
     // The inter-pass block of a chunk is written by pass 1 and read back by pass 2 right away: chunks are sized to stay
-    // in L2 (l2_block_budget), so HBM sees 32 B per point, not 64. Chunks alternate between two streams (two scratch
-    // blocks), which hides the launch gaps and tails of these short launches behind the other chunk's kernels.
+    // in L2 (l2_block_budget), so HBM sees 32 B per point, not 64. Chunks rotate over chunk_streams streams (one scratch
+    // block each), which hides the launch gaps and tails of these short launches behind the other chunks' kernels.
     const size_t budget = d.pass_scratch_budget < d.l2_block_budget ? d.pass_scratch_budget : d.l2_block_budget;
     long long chunk = (long long)(budget / ((size_t)N * sizeof(cpx)));
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
-    const bool two = d.two_stream_chunks && batch >= 4 * chunk;
+    const long long nchunks = (batch + chunk - 1) / chunk;
+    ForkJoin fj(d, st, nchunks >= 2 * d.chunk_streams ? d.chunk_streams : 1);
     cpx* scr0;
-    GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)(two ? 2 : 1) * chunk * N * sizeof(cpx), (void**)&scr0));
+    GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)fj.ways * chunk * N * sizeof(cpx), (void**)&scr0));
     const bool real_in = ops.ld_flags & LD_REAL;
-    ForkJoin fj(d, st, two);
-    if (batch > chunk) fj.persist(scr0, (size_t)(two ? 2 : 1) * chunk * N * sizeof(cpx));
+    if (nchunks > 1) fj.persist(scr0, (size_t)fj.ways * chunk * N * sizeof(cpx));
     long long ci = 0;
     for (long long b0 = 0; b0 < batch; b0 += chunk, ci++) {
         long long nb = batch - b0 < chunk ? batch - b0 : chunk;
         cudaStream_t st = fj.stream(ci);
-        cpx* scr = scr0 + (two && (ci & 1) ? (size_t)chunk * N : 0);
+        cpx* scr = scr0 + (size_t)fj.way(ci) * chunk * N;
         // pass 1: columns n2 of every transform, length N1, twiddle w_N^(n2*k1) on store; the intermediate
         // is tile-major (T adjacent columns = one contiguous block) so these stores are fully coalesced
         const bool lean32 = d.w32 >= 1 && d.w32 <= 6 && !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
@@ -815,22 +826,22 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         const long long R1 = 1LL << l1, R2 = 1LL << l2;
         TwiddleTable tw;
         GD_TRY(d.twiddles(lg, &tw));
-        // blocks sized to stay in L2 between the passes, alternating between two streams (see fft_pow2)
+        // blocks sized to stay in L2 between the passes, rotating over several streams (see fft_pow2)
         const size_t budget = d.pass_scratch_budget < d.l2_block_budget ? d.pass_scratch_budget : d.l2_block_budget;
         long long cb = (long long)(budget / ((size_t)len * sizeof(cpx)));
         if (cb < 8) cb = 8;
         if (cb > s) cb = s;
-        const bool two = d.two_stream_chunks && outer * ((s + cb - 1) / cb) >= 4;
+        const long long nblocks = outer * ((s + cb - 1) / cb);
+        ForkJoin fj(d, st, nblocks >= 2 * d.chunk_streams ? d.chunk_streams : 1);
         cpx* scr0;
-        GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)(two ? 2 : 1) * len * cb * sizeof(cpx), (void**)&scr0));
-        ForkJoin fj(d, st, two);
-        if (outer * ((s + cb - 1) / cb) > 1) fj.persist(scr0, (size_t)(two ? 2 : 1) * len * cb * sizeof(cpx));
+        GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)fj.ways * len * cb * sizeof(cpx), (void**)&scr0));
+        if (nblocks > 1) fj.persist(scr0, (size_t)fj.ways * len * cb * sizeof(cpx));
         long long ci = 0;
         for (long long o = 0; o < outer; o++)
             for (long long c0 = 0; c0 < s; c0 += cb, ci++) {
                 long long nc = s - c0 < cb ? s - c0 : cb;
                 cudaStream_t st = fj.stream(ci);
-                cpx* scr = scr0 + (two && (ci & 1) ? (size_t)len * cb : 0);
+                cpx* scr = scr0 + (size_t)fj.way(ci) * len * cb;
                 const cpx* sp = src + o * len * s + c0;
                 cpx* dp = dst + o * len * s + c0;
                 // pass 1: lines (n2, c): length R1 over n1 (stride R2*s); out block[(k1*R2 + n2)][c]

@@ -71,16 +71,18 @@ struct Device {
     cudaStream_t stream = nullptr;       // compute stream of the host-pointer entry points
     cudaStream_t stream_in = nullptr;    // H2D
     cudaStream_t stream_out = nullptr;   // D2H
-    cudaStream_t stream_aux = nullptr;   // every other L2-sized chunk of a multi-pass transform (ForkJoin, engine.cu)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    static constexpr int AUX_STREAMS = 3;
+    cudaStream_t stream_aux[AUX_STREAMS] = {nullptr};   // the other L2-sized chunks of a multi-pass transform (ForkJoin, engine.cu)
+    cudaEvent_t ev_fork = nullptr, ev_join[AUX_STREAMS] = {nullptr};
     cpx* wl[13] = {nullptr};             // intra-line tables exp(-2 pi i e/L), L = 2^k
     std::map<int, TwiddleTable> tw;      // keyed by log2 M
     std::map<long long, BluesteinPlan> blue;
     void* scratch[SCR_NSLOTS] = {nullptr};
     size_t scratch_bytes[SCR_NSLOTS] = {0};
     size_t pass_scratch_budget = 1ull << 30;    // upper bound of the inter-pass scratch of the two-launch four-step path
-    size_t l2_block_budget = 32ull << 20;       // inter-pass block of one chunk: small enough to stay in L2 between the passes
-    bool two_stream_chunks = true;              // alternate chunks between two streams
+    size_t l2_block_budget = 24ull << 20;       // inter-pass block of one chunk: small enough to stay in L2 between the passes
+    bool pwelch_bulk = true;                    // L = 4096 float64: bulk-copy fed kernel (pwelch.cu)
+    int chunk_streams = 2;                      // streams the chunks of one call rotate over (1 .. 1 + AUX_STREAMS)
     bool l2_block_window = true;                // persisting L2 window over the inter-pass blocks of a chunked call
     bool l2_hold = false;                       // a chunked call is in flight: keep the set-aside between its launches
     bool wide_tiles = false;             // 512-thread tiles for L >= 1024

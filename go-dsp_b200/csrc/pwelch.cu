@@ -148,6 +148,113 @@ pwelch_fused_kernel(const void* __restrict__ xv, long long nfft, long long strid
     for (int i = 0; i < 16; i++) partial[gg * L + p + P * i] = acc[i];
 }
 
+// ---- bulk-fed kernel for L = 4096 (config C4) --------------------------------------------------------------------------
+// Same arithmetic as pwelch_fused_kernel<12>, different plumbing. The load/store unit is this kernel's co-limiting
+// pipe (ncu: 59 % of its wavefront rate against 52 % of the FP64 pipe), so the sample ranges no longer pass through
+// it on the way in: one thread issues ONE bulk copy per segment pair (cp.async.bulk, the TMA engine, completion on an
+// mbarrier) into a staging buffer of its own, as soon as the previous pair's samples have been taken -- a whole
+// iteration ahead, instead of 24 LDGSTS per thread issued late in the iteration. The exchange buffer is unpadded
+// (element i lives at i ^ ((i >> 4) & 7): radix-16 scatters and gathers stay conflict-free), which is what makes
+// 64 KiB + 48 KiB fit twice per SM; four CTA-wide barriers per pair instead of six; with 50 % overlap the second
+// segment's first half IS the first segment's second half, so 8 of the 32 staged loads per thread are not repeated.
+constexpr int PWB_L = 4096, PWB_P = 256;
+constexpr int PWB_STAGE_DOUBLES = 2 * PWB_L;                                    // stride + nfft <= 2 L samples per pair
+constexpr int PWB_SMEM = PWB_L * 16 + PWB_STAGE_DOUBLES * 8 + 64;               // exchange + staging + mbarrier
+
+__device__ __forceinline__ unsigned pw_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(PWB_P, 2)
+pwelch_bulk_kernel(const double* __restrict__ x, long long nfft, long long stride, long long seg0, long long nseg,
+                   const double* __restrict__ win, double* __restrict__ partial, const cpx* __restrict__ wl) {
+    constexpr int L = PWB_L, P = PWB_P;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cpx* sl = reinterpret_cast<cpx*>(smem_raw);
+    double* stage = reinterpret_cast<double*>(smem_raw + L * 16);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + L * 16 + PWB_STAGE_DOUBLES * 8);
+    const int p = threadIdx.x;
+    const long long npairs = (nseg + 1) / 2;
+    const long long u0 = (long long)blockIdx.x * npairs / gridDim.x, u1 = ((long long)blockIdx.x + 1) * npairs / gridDim.x;
+    const bool half_overlap = (2 * stride == nfft) && nfft == L;
+
+    if (p == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(pw_smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto fetch = [&](long long u) {               // thread 0: one bulk copy of the pair's sample range
+        const long long count = (2 * u + 1 < nseg) ? stride + nfft : nfft;
+        const unsigned bytes = (unsigned)(count * 8);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(pw_smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(pw_smem_u32(stage)), "l"(x + (seg0 + 2 * u) * stride), "r"(bytes), "r"(pw_smem_u32(bar)) : "memory");
+    };
+    if (p == 0 && u0 < u1) fetch(u0);
+
+    // exchange addressing: element i at i ^ ((i >> 4) & 7)
+    const int m1 = p & 7;                         // scatter 1: i = 16 p + r            -> 16 p + (r ^ m1)
+    cpx* sc1 = sl + 16 * p;
+    const int k2 = p & 15;                        // scatter 2: i = 256 (p >> 4) + k2 + 16 r -> low bits k2 ^ (r & 7)
+    cpx* sc2 = sl + 16 * (p - k2);
+    const cpx* ga = sl + (p ^ ((p >> 4) & 7));    // gathers: i = p + 256 q                -> (p ^ c) + 256 q
+
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = 0.0;
+    unsigned phase = 0;
+    for (long long u = u0; u < u1; u++) {
+        const bool has_b = 2 * u + 1 < nseg;
+        {   // the pair's samples have landed
+            asm volatile(
+                "{\n.reg .pred q;\nPW_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n@q bra PW_DONE_%=;\nbra PW_WAIT_%=;\nPW_DONE_%=:\n}\n"
+                ::"r"(pw_smem_u32(bar)), "r"(phase) : "memory");
+            phase ^= 1u;
+        }
+        cpx z[16];
+        if (half_overlap && has_b) {
+            double a[24];
+#pragma unroll
+            for (int i = 0; i < 24; i++) a[i] = stage[p + P * i];          // samples p + 256 i of the 6144-sample range
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const double w = __ldg(win + p + P * i);
+                z[i] = make_double2(w * a[i], w * a[i + 8]);              // b[n] = range[n + 2048]
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int n = p + P * i;
+                double a = 0.0, b = 0.0, w = 0.0;
+                if (n < nfft) {
+                    w = __ldg(win + n);
+                    a = stage[n];
+                    if (has_b) b = stage[stride + n];
+                }
+                z[i] = make_double2(w * a, w * b);
+            }
+        }
+        __syncthreads();                          // staging consumed; the previous pair's gathers are done as well
+        if (p == 0 && u + 1 < u1) fetch(u + 1);
+        butterfly_step<L, 16, 1>(z, p, wl);
+#pragma unroll
+        for (int r = 0; r < 16; r++) sc1[r ^ m1] = z[r];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; q++) z[q] = ga[P * q];
+        butterfly_step<L, 16, 16>(z, p, wl);
+        __syncthreads();                          // every gather of the first exchange is done
+#pragma unroll
+        for (int r = 0; r < 16; r++) sc2[16 * r + (k2 ^ (r & 7))] = z[r];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; q++) z[q] = ga[P * q];
+        butterfly_step<L, 16, 256>(z, p, wl);
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = fma(z[i].x, z[i].x, fma(z[i].y, z[i].y, acc[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) partial[(long long)blockIdx.x * L + p + P * i] = acc[i];
+}
+
 // raw[j] = 0.5 * (S[j] + S[(L-j) mod L]),  S[k] = sum over groups (fixed order) of partial[g][k]
 __global__ void pwelch_fold_kernel(const double* __restrict__ partial, long long groups, int L, long long lp,
                                    double* __restrict__ raw) {
@@ -215,6 +322,30 @@ static Status launch_fused(Device& d, const void* x, int fmt, long long nfft, lo
                   : fmt == SMP_F32 ? (PwKernel)pwelch_fused_kernel<LOG2L, false, SMP_F32>
                   : fmt == SMP_S16 ? (PwKernel)pwelch_fused_kernel<LOG2L, false, SMP_S16>
                                    : (PwKernel)pwelch_fused_kernel<LOG2L, false, SMP_U8>;
+    if constexpr (LOG2L == 12) {
+        // config C4's shape: float64, nfft = 4096, aligned ranges of an even number of samples -> the bulk-fed kernel
+        if (aligned && d.pwelch_bulk && nfft == 4096 && (stride % 2) == 0) {
+            static int bulk_bps[16] = {0};
+            int& b = bulk_bps[d.dev & 15];
+            if (!b) {
+                GD_CUDA(cudaFuncSetAttribute(pwelch_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PWB_SMEM));
+                GD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, pwelch_bulk_kernel, PWB_P, PWB_SMEM));
+                if (b < 1) { set_error("pwelch_bulk_kernel does not fit on an SM"); return GD_ERR_CUDA; }
+            }
+            const long long npairs = (nseg + 1) / 2;
+            long long grid = (long long)d.num_sms * b;
+            if (grid > npairs) grid = npairs;
+            double* partial;
+            GD_TRY(d.ensure_scratch(SCR_PWELCH, (size_t)grid * PWB_L * sizeof(double), (void**)&partial));
+            pwelch_bulk_kernel<<<(unsigned)grid, PWB_P, PWB_SMEM, st>>>((const double*)x, nfft, stride, seg0, nseg, win, partial, d.wl[12]);
+            g_launches++;
+            GD_CUDA(cudaGetLastError());
+            pwelch_fold_kernel<<<(unsigned)((lp + 127) / 128), 128, 0, st>>>(partial, grid, PWB_L, lp, raw);
+            g_launches++;
+            GD_CUDA(cudaGetLastError());
+            return GD_OK;
+        }
+    }
     const int threads = SH::T * SH::P, smem = SH::T * SH::LS * (int)sizeof(cpx);
     static int bps[5][16] = {{0}};                       // per (variant, device): the opt-in below is a per-device attribute
     int& blocks_per_sm = bps[aligned ? 4 : fmt][d.dev & 15];
