@@ -18,6 +18,11 @@ bool tma_fused_applicable(const void* in, long long in_dist, const cpx* out, lon
 Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long batch, int ld_conj,
                     int st_conj, double scale, cudaStream_t st);
 int pass32_tile_lines(int variant);
+bool tma14_rows_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, long long batch, int ld_conj, int st_conj,
+                           double scale);
+bool tma14_cols_applicable(const cpx* src, const cpx* dst, long long len, long long s);
+Status fft_tma_2p14(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
+                    cudaStream_t st);
 
 // ------------------------------------------------------------------ errors
 std::atomic<long long> g_launches{0};
@@ -294,6 +299,12 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
         if (tma_fused_applicable(in, in_dist, out, out_dist, lc, sc, scl))
             return fft_tma_2p20(d, (const cpx*)in, in_dist, out, out_dist, batch, lc, sc, scl, st);
+    }
+    if (d.use_tma && d.use_tma14 && lean && log2n == 14 && !d.debug_alias) {
+        const int lc = (ops.ld_flags & LD_CONJ) ? 1 : 0, sc = (ops.st_flags & ST_CONJ) ? 1 : 0;
+        const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
+        if (tma14_rows_applicable(in, in_dist, out, out_dist, batch, lc, sc, scl))
+            return fft_tma_2p14(d, 0, (const cpx*)in, in_dist, out, out_dist, batch, lc != 0, scl, st);
     }
     if (d.use_fused && lean && (log2n % 2) == 0 && log2n >= 16 && batch * (2LL << (log2n / 2)) < (1LL << 30)) {
         // both passes in one persistent kernel, intermediate resident in L2 (fft_fused.cuh)
@@ -819,6 +830,12 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         p.in_mode = p.out_mode = MODE_COL;
         if (dir < 0) { p.ld_flags = LD_CONJ; p.st_flags = ST_CONJ | ST_SCALE; p.scale = 1.0 / (double)len; }
         return launch_pass(d, l, p, st);
+    }
+    if (d.use_tma && d.use_tma14 && tma14_cols_applicable(src, dst, len, s)) {
+        // every column of a 2^14-row matrix: one fused launch, intermediate resident in L2 (fft_tma14.cuh)
+        for (long long o = 0; o < outer; o++)
+            GD_TRY(fft_tma_2p14(d, 1, src + o * len * s, 0, dst + o * len * s, 0, s, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
+        return GD_OK;
     }
     if (p2 && len <= (1LL << 24) && fits31) {
         // strided four-step on blocks of cb adjacent columns; the inter-pass block [len][cb] stays in L2

@@ -98,6 +98,7 @@ struct Device {
     bool use_fused = false;              // one persistent kernel for both four-step passes (N = L*L), L2-resident scratch
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)
+    bool use_tma14 = true;               // 2^14-point lines (batched rows, columns of a 2^14-row matrix): fused kernel of fft_tma14.cuh
     int tma_opt = 0;                     // measurement switches of the fused kernel (TmaFusedParams::opt)
     int tma_prof = 0;                    // measurement: cycle counters of the fused kernel (gd_tma_profile_read)
     int tma_delay = 2;                   // P1 phases the schedule runs ahead of P2 (fft_tma.cuh)

@@ -1,0 +1,325 @@
+// fft_tma14.cuh -- 2^14-point complex128 transforms (the lines of fft.FFT2 on a 16384 x 16384 matrix, config C3, and any
+// batch of 2^14-point transforms) as ONE persistent, TMA-fed launch per axis: both passes of the N = 128 x 128 four-step,
+// intermediate resident in L2. Same machinery as fft_tma.cuh (in-order tile queue, loader / storer / watcher lanes,
+// D = 2 phases of pass-1 run-ahead over S = 3 scratch slots of 16 MiB); what differs is the tile and the arithmetic.
+// Replaces, per axis, the two launches of the pass kernel whose inter-pass array went through HBM
+// (fft/fft.go:138-151 is two sweeps of 14 radix-2 stages each in the reference).
+//
+// A tile is 32 adjacent lines of 128 points: 128 rows x 32 complex (512 contiguous bytes), landing in halves of 64 rows.
+//   ROWS (transform t contiguous, x[t][128 n1 + n2]):   lines = 32 adjacent n2 (pass 1) / 32 adjacent k1 (pass 2)
+//       P1: rows n1 of x[t]          -> Int[t][n2][k1] (32 rows of 2 KiB, one bulk copy each)
+//       P2: rows n2 of Int[t][.][k1] -> X[t][k1 + 128 k2] (tile store)
+//   COLS (transform = column t of a row-major R x C matrix, R = 2^14): lines = 32 adjacent columns t in both passes
+//       P1: rows n1 of M[128 n1 + n2][t]   -> Int[tb][n2][k1][32 t] (64 KiB contiguous)
+//       P2: rows n2 of Int[tb][.][k1][.]   -> M'[k1 + 128 k2][t]
+// A phase (the unit of the dependency counters) is 256 tiles = 2^20 points = one 16 MiB slot: 64 transforms (ROWS) or
+// 64 columns (COLS).
+// Consumer group = 4 warps: lane = line, warp j = residue of the point index mod 4. 128 = 32 x 4: a radix-32 step on
+// points j + 4 i, the twiddle w_128^(j k) (warp-uniform, read from the kernel parameters: no product chains), one
+// shared-memory exchange, eight radix-4 butterflies.
+#pragma once
+#include "fft_tma.cuh"
+
+namespace gd {
+
+constexpr int T14_LINES = 32, T14_LEN = 128;
+constexpr int T14_HALF_BYTES = 64 * T14_LINES * 16;                   // 32768
+constexpr int T14_ROWPITCH = T14_LEN + 1;                             // ROWS pass-1 staging: 32 rows of 129 elements (skew: conflict-free)
+constexpr int T14_WBYTES = T14_LINES * T14_ROWPITCH * 16;             // 66048 >= 65536
+constexpr int T14_WELEMS = T14_WBYTES / 16;
+constexpr int T14_SMEM = TMA_NSLOT * T14_HALF_BYTES + 2 * T14_WBYTES + 1024;     // 231424
+enum : int { T14_ROWS = 0, T14_COLS = 1 };
+
+struct Tma14Params {
+    int batch;                   // phases (groups of 256 tiles) in this launch
+    int delay, nslots;
+    cpx* scratch;                // nslots slots of 2^20 elements
+    int* done1;
+    int* done2;
+    int* queue;
+    const cpx* tw_lo;            // w_16384^e = hi[e >> 12] * lo[e & 4095]
+    const cpx* tw_hi;
+    double scale;                // inverse: 1/N folded into the four-step twiddle
+    cpx w128[3][32];             // w_128^(j k), j = 1..3, k < 32
+};
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3, const void* src) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src)) : "memory");
+}
+
+// tile c of phase (type, grp), half h -> tensor coordinates (in doubles along dim 0)
+template <int MODE>
+__device__ __forceinline__ void t14_coords(int type, int grp, int c, int h, int S, int& c0, int& c1, int& c2, int& c3, bool in) {
+    if constexpr (MODE == T14_ROWS) {
+        const int tl = c >> 2, q = c & 3;                 // transform within the group, block of 32 lines
+        c0 = 64 * q; c1 = 64 * h; c3 = 0;
+        c2 = (type == 1 && in) ? (grp % S) * 64 + tl : grp * 64 + tl;
+    } else {
+        const int tbl = c >> 7, r = c & 127;              // t-block within the group (2), n2 (pass 1) or k1 (pass 2)
+        if (type == 1 && in) { c0 = 0; c1 = r; c2 = 64 * h; c3 = (grp % S) * 2 + tbl; }
+        else { c0 = 64 * (grp * 2 + tbl); c1 = r; c2 = 64 * h; c3 = 0; }
+    }
+}
+
+template <int MODE, bool INV>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_int,
+                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ Tma14Params a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    cpx* land = reinterpret_cast<cpx*>(smem_raw);
+    cpx* work = reinterpret_cast<cpx*>(smem_raw + TMA_NSLOT * T14_HALF_BYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + TMA_NSLOT * T14_HALF_BYTES + 2 * T14_WBYTES);
+    unsigned long long* full_h = bars;                     // [3 slots][2 groups]
+    unsigned long long* freed_h = bars + 6;                // [3]
+    unsigned long long* rd = bars + 9;                     // [2]
+    unsigned long long* staged = bars + 11;                // [2]
+    unsigned long long* drained = bars + 13;               // [2 groups][2 halves of the work buffer]
+    volatile int* log = reinterpret_cast<volatile int*>(bars + 22);        // [32]
+    volatile int* log_count = reinterpret_cast<volatile int*>(bars + 38);
+    volatile int* ready_sh = reinterpret_cast<volatile int*>(bars + 39);
+    constexpr int TPT = 256;                               // tiles per phase
+    constexpr int HALF_ELEMS = T14_HALF_BYTES / 16;        // 2048
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < 6; i++) mbar_init(full_h + i, 1);
+        for (int i = 0; i < 3; i++) mbar_init(freed_h + i, TMA_GROUP);
+        for (int i = 0; i < 2; i++) { mbar_init(rd + i, TMA_GROUP); mbar_init(staged + i, TMA_GROUP); }
+        for (int i = 0; i < 4; i++) mbar_init(drained + i, 1);
+        *log_count = 0;
+        *ready_sh = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int B = a.batch, D = a.delay, S = a.nslots;
+    const int nitems = 2 * B * TPT;
+
+    if (warp >= 2 * TMA_GROUP / 32) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (tid == 2 * TMA_GROUP) {
+            // ------------------------------------------------------------ loader (see fft_tma.cuh)
+            int tokens = 0, ready_tf = -1;
+            long long hidx = 0;
+            int cur = atomicAdd(a.queue, 2);
+            for (int it = 0; tokens < 2; it++) {
+                if (hidx >= TMA_NSLOT) mbar_wait(freed_h + (int)(hidx % TMA_NSLOT), (unsigned)(((hidx - TMA_NSLOT) / TMA_NSLOT) & 1));
+                const int item = tokens ? nitems : cur + (it & 1);
+                const bool token = item >= nitems;
+                TmaItem w;
+                w.type = 0; w.tf = 0; w.c = 0;
+                if (!token) {
+                    w = tma_decode(item, B, D);
+                    if (w.type == 1 && w.tf > ready_tf) {
+                        while (ld_volatile_shared(ready_sh) <= w.tf) __nanosleep(20);
+                        __threadfence_block();
+                        asm volatile("fence.proxy.async;\n" ::: "memory");
+                        ready_tf = ld_volatile_shared(ready_sh) - 1;
+                    }
+                }
+                log[it & 31] = token ? -1 : item;
+                __threadfence_block();
+                *log_count = it + 1;
+                if (token) tokens++;
+#pragma unroll
+                for (int h = 0; h < 2; h++, hidx++) {
+                    const int s = (int)(hidx % TMA_NSLOT);
+                    if (token && h == 1) continue;
+                    if (h == 1 && hidx >= TMA_NSLOT) mbar_wait(freed_h + s, (unsigned)(((hidx - TMA_NSLOT) / TMA_NSLOT) & 1));
+                    unsigned long long* fb = full_h + 2 * s + (it & 1);
+                    if (token) { mbar_arrive(fb); continue; }
+                    mbar_expect_tx(fb, T14_HALF_BYTES);
+                    int c0, c1, c2, c3;
+                    t14_coords<MODE>(w.type, w.tf, w.c, h, S, c0, c1, c2, c3, true);
+                    tma_load_4d(land + (size_t)s * HALF_ELEMS, w.type == 0 ? &tm_x : &tm_int, c0, c1, c2, c3, fb);
+                }
+                if (!tokens && (it & 1)) cur = atomicAdd(a.queue, 2);
+            }
+        } else if (tid == 2 * TMA_GROUP + 96) {
+            // ------------------------------------------------------------ watcher
+            for (int tf = 0; tf < B; tf++) {
+                while (ld_relaxed_gpu(a.done1 + tf) < TPT) __nanosleep(64);
+                asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+                asm volatile("fence.proxy.async;\n" ::: "memory");
+                *ready_sh = tf + 1;
+            }
+        } else if (tid == 2 * TMA_GROUP + 32 || tid == 2 * TMA_GROUP + 64) {
+            // ------------------------------------------------------------ storer of consumer group g
+            const int g = tid == 2 * TMA_GROUP + 32 ? 0 : 1;
+            const unsigned long long pol_last = policy_evict_last();
+            unsigned ns = 0;
+            int free_tf = S - 1;
+            for (int it = g;; it += 2) {
+                while (ld_volatile_shared(log_count) <= it) __nanosleep(64);
+                __threadfence_block();
+                const int item = log[it & 31];
+                if (item < 0) break;
+                const TmaItem pi = tma_decode(item, B, D);
+                mbar_wait(staged + g, ns & 1);
+                ns++;
+                const cpx* srcb = work + (size_t)g * T14_WELEMS;
+                if (pi.type == 1) {
+                    int c0, c1, c2, c3;
+                    t14_coords<MODE>(1, pi.tf, pi.c, 0, S, c0, c1, c2, c3, false);
+                    tma_store_4d(&tm_out, c0, c1, c2, c3, srcb);
+                    tma_commit();
+                    t14_coords<MODE>(1, pi.tf, pi.c, 1, S, c0, c1, c2, c3, false);
+                    tma_store_4d(&tm_out, c0, c1, c2, c3, srcb + HALF_ELEMS);
+                    tma_commit();
+                } else {
+                    if (pi.tf > free_tf) {
+                        while (ld_relaxed_gpu(a.done2 + (pi.tf - S)) < TPT) __nanosleep(32);
+                        free_tf = pi.tf;
+                    }
+                    cpx* slot = a.scratch + (size_t)(pi.tf % S) * ((size_t)1 << 20);
+                    if constexpr (MODE == T14_ROWS) {
+                        // Int[t][n2 = 32 q + ell][k1]: 32 rows of 2 KiB, contiguous in memory, 129-element pitch in shared memory
+                        cpx* dst = slot + (size_t)(pi.c >> 2) * 16384 + (size_t)(pi.c & 3) * 32 * T14_LEN;
+#pragma unroll 1
+                        for (int l = 0; l < 16; l++) bulk_store_1d_hint(dst + l * T14_LEN, srcb + l * T14_ROWPITCH, T14_LEN * 16, pol_last);
+                        tma_commit();
+#pragma unroll 1
+                        for (int l = 16; l < 32; l++) bulk_store_1d_hint(dst + l * T14_LEN, srcb + l * T14_ROWPITCH, T14_LEN * 16, pol_last);
+                        tma_commit();
+                    } else {
+                        // Int[tb][n2][k1][32 t]: the tile is 64 KiB contiguous
+                        cpx* dst = slot + ((size_t)(pi.c >> 7) * 128 + (size_t)(pi.c & 127)) * (T14_LEN * T14_LINES);
+                        bulk_store_1d_hint(dst, srcb, T14_HALF_BYTES, pol_last);
+                        tma_commit();
+                        bulk_store_1d_hint(dst + HALF_ELEMS, srcb + HALF_ELEMS, T14_HALF_BYTES, pol_last);
+                        tma_commit();
+                    }
+                }
+                tma_wait_read1();
+                mbar_arrive(drained + 2 * g);
+                tma_wait_read0();
+                mbar_arrive(drained + 2 * g + 1);
+                if (pi.type == 0) {
+                    tma_wait_all0();
+                    asm volatile("fence.proxy.async.global;\n" ::: "memory");
+                    red_release_gpu(a.done1 + pi.tf, 1);
+                }
+            }
+            tma_wait_all0();
+        }
+        return;
+    }
+
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    const int g = warp >> 2;
+    const int j = warp & 3, ell = tid & 31;                 // point residue mod 4 (warp-uniform), line
+    cpx* wbuf = work + (size_t)g * T14_WELEMS;
+    unsigned nrd = 0, nst = 0;
+    bool first = true;
+    unsigned fph = 0;
+    for (int it = g;; it += 2) {
+        const long long h0 = 2LL * it;
+        const int s0 = (int)(h0 % TMA_NSLOT), s1 = (int)((h0 + 1) % TMA_NSLOT);
+        mbar_wait(full_h + 2 * s0 + g, (fph >> s0) & 1);
+        fph ^= 1u << s0;
+        const int item = log[it & 31];
+        if (item < 0) break;
+        const TmaItem wi = tma_decode(item, B, D);
+        const unsigned ld_conj = (INV && wi.type == 0) ? 0x80000000u : 0u;
+        cpx x[32];
+        {   // points j + 4 i of line ell: rows j + 4 i of the tile, i < 16 in the first half
+            const cpx* s = land + (size_t)s0 * HALF_ELEMS + j * T14_LINES + ell;
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = INV ? cconj_if(s[i * 4 * T14_LINES], ld_conj) : s[i * 4 * T14_LINES];
+        }
+        mbar_arrive(freed_h + s0);
+        mbar_wait(full_h + 2 * s1 + g, (fph >> s1) & 1);
+        fph ^= 1u << s1;
+        if (wi.type == 1 && tid == g * TMA_GROUP) red_relaxed_gpu(a.done2 + wi.tf, 1);
+        {
+            const cpx* s = land + (size_t)s1 * HALF_ELEMS + j * T14_LINES + ell;
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[16 + i] = INV ? cconj_if(s[i * 4 * T14_LINES], ld_conj) : s[i * 4 * T14_LINES];
+        }
+        mbar_arrive(freed_h + s1);
+        dft32(x);                                           // Y_j[k] = sum_i x[j + 4 i] w_32^(i k)
+        if (j != 0) {                                       // warp-uniform: w_128^(j k) from the parameter bank
+#pragma unroll
+            for (int k = 1; k < 32; k++) x[k] = cmul(x[k], a.w128[j - 1][k]);
+        }
+        if (!first) mbar_wait(drained + 2 * g, (nst - 1) & 1);
+        // exchange: Y_j[k] -> row 4 k + j of the work buffer, column ell; thread (ell, j') then takes rows 32 j' .. 32 j' + 31,
+        // i.e. k = 8 j' + k_lo, all four j
+        {
+            cpx* s = wbuf + j * T14_LINES + ell;
+#pragma unroll
+            for (int k = 0; k < 16; k++) s[k * 4 * T14_LINES] = x[k];                        // rows < 64
+            if (!first) mbar_wait(drained + 2 * g + 1, (nst - 1) & 1);
+#pragma unroll
+            for (int k = 16; k < 32; k++) s[k * 4 * T14_LINES] = x[k];
+        }
+        first = false;
+        // four-step twiddle bases of this line (pass 1): w^(n2 * 8 j'), w^(n2), w^(32 n2)
+        cpx tb0, tb1, tb32;
+        if (wi.type == 0) {
+            const unsigned n2 = MODE == T14_ROWS ? (unsigned)((wi.c & 3) * 32 + ell) : (unsigned)(wi.c & 127);
+            const unsigned e0 = (n2 * 8u * (unsigned)j) & 16383u, e1 = n2 & 16383u, e32 = (n2 * 32u) & 16383u;
+            tb0 = cmul(__ldg(a.tw_hi + (e0 >> 12)), __ldg(a.tw_lo + (e0 & 4095u)));
+            tb1 = cmul(__ldg(a.tw_hi + (e1 >> 12)), __ldg(a.tw_lo + (e1 & 4095u)));
+            tb32 = cmul(__ldg(a.tw_hi + (e32 >> 12)), __ldg(a.tw_lo + (e32 & 4095u)));
+            if (INV) tb0 = make_double2(tb0.x * a.scale, tb0.y * a.scale);
+        }
+        group_bar(1 + g);
+        {
+            const cpx* s = wbuf + (32 * j) * T14_LINES + ell;
+#pragma unroll
+            for (int r = 0; r < 32; r++) x[r] = s[r * T14_LINES];                            // x[4 k_lo + jj] = Y_jj[8 j + k_lo]
+        }
+        mbar_arrive(rd + g);
+#pragma unroll
+        for (int kl = 0; kl < 8; kl++) dft4<1>(&x[4 * kl]);                                  // x[4 k_lo + m] = X[8 j + k_lo + 32 m]
+        mbar_wait(rd + g, nrd & 1);                         // every gather of this tile is done: the buffer may be overwritten
+        nrd++;
+        if (wi.type == 0) {
+            // x[4 k_lo + m] *= w^(n2 (8 j + k_lo + 32 m)) = tb0 * tb1^k_lo * tb32^m
+            cpx c[8];
+            c[0] = tb0;
+#pragma unroll
+            for (int kl = 1; kl < 8; kl++) c[kl] = cmul(c[kl - 1], tb1);
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+#pragma unroll
+                for (int kl = 0; kl < 8; kl++) {
+                    x[4 * kl + m] = cmul(x[4 * kl + m], c[kl]);
+                    if (m < 3) c[kl] = cmul(c[kl], tb32);
+                }
+            }
+            if constexpr (MODE == T14_ROWS) {
+                cpx* s = wbuf + ell * T14_ROWPITCH + 8 * j;  // Int[n2 = line][k1 = 8 j + k_lo + 32 m]
+#pragma unroll
+                for (int kl = 0; kl < 8; kl++)
+#pragma unroll
+                    for (int m = 0; m < 4; m++) s[kl + 32 * m] = x[4 * kl + m];
+            } else {
+                cpx* s = wbuf + (8 * j) * T14_LINES + ell;   // Int[k1][32 t]: row k1, column = line
+#pragma unroll
+                for (int kl = 0; kl < 8; kl++)
+#pragma unroll
+                    for (int m = 0; m < 4; m++) s[(kl + 32 * m) * T14_LINES] = x[4 * kl + m];
+            }
+        } else {
+            cpx* s = wbuf + (8 * j) * T14_LINES + ell;       // X[k2 = 8 j + k_lo + 32 m]: row k2 of the tile, column = line
+#pragma unroll
+            for (int kl = 0; kl < 8; kl++)
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const cpx v = x[4 * kl + m];
+                    s[(kl + 32 * m) * T14_LINES] = INV ? make_double2(v.x, -v.y) : v;
+                }
+        }
+        fence_proxy_async();
+        mbar_arrive(staged + g);
+        nst++;
+    }
+}
+
+}  // namespace gd

@@ -260,6 +260,24 @@ def test_fft2_large_rows_cols(gd):               # 2^14-long lines in both axes 
         assert rel_l2(out, oracle.fft2(x)) <= TOL
 
 
+@pytest.mark.parametrize("rows,cols", [(16384, 128), (256, 16384), (16384, 320), (192, 16384)])
+def test_fft2_fused_2p14_lines(gd, rows, cols):  # the fused 2^14 kernel (fft_tma14.cuh): columns of a 2^14-row matrix, batched 2^14 rows
+    _, capi, L = gd
+    x = oracle.splitmix_complex(rows * cols, 4).reshape(rows, cols)
+    out, back = np.empty_like(x), np.empty_like(x)
+    capi.check(L.gd_fft2_c2c(x.ctypes.data, out.ctypes.data, rows, cols, 1))
+    assert rel_l2(out, oracle.fft2(x)) <= TOL
+    capi.check(L.gd_fft2_c2c(out.ctypes.data, back.ctypes.data, rows, cols, -1))
+    assert rel_l2(back, x) <= TOL
+    capi.check(L.gd_set_option(b"tma14", 0))     # and the two-launch schedule gives the same result
+    try:
+        o2 = np.empty_like(x)
+        capi.check(L.gd_fft2_c2c(x.ctypes.data, o2.ctypes.data, rows, cols, 1))
+    finally:
+        capi.check(L.gd_set_option(b"tma14", 1))
+    assert rel_l2(o2, out) <= 1e-14
+
+
 def test_fft2_16384_square_sampled(gd):          # config C3: the full 16384 x 16384 matrix, device resident
     """Output rows / columns of the full-size result against oracle.fft of the matching single-bin DFT of the other axis
     (a float64 matrix-vector product with exactly reduced phasors, computed by torch -- not by this library):

@@ -12,7 +12,7 @@ out = torch.empty_like(src)
 capi.check(L.gd_fill_splitmix_dev(src.data_ptr(), 2 * R * Cc, 4, 0, None)); capi.check(L.gd_stream_sync(None))
 dims = (C.c_int64 * 2)(R, Cc)
 st = torch.cuda.Stream(); sp = st.cuda_stream
-DEFAULTS = {"l2_block_mb": 24, "chunk_streams": 2, "pass_scratch_mb": 1024, "l2_block_window": 1}
+DEFAULTS = {"l2_block_mb": 24, "chunk_streams": 2, "pass_scratch_mb": 1024, "l2_block_window": 1, "tma14": 1}
 for combo in (sys.argv[1:] or [""]):
     for k0, v0 in DEFAULTS.items():
         capi.check(L.gd_set_option(k0.encode(), v0))
