@@ -51,7 +51,7 @@ def parse():
 # --------------------------------------------------------------------------- helpers
 def ncu_traffic(kernel_substr):
     """dram read+write bytes per launch of a kernel, from the committed ncu --set full summary (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")
+    p = os.path.join(ROOT, "profiles", "r2_ncu_full_summary.json")
     try:
         with open(p) as f:
             rows = [r for r in json.load(f) if kernel_substr in r.get("Kernel Name", "")]
@@ -74,6 +74,40 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def fp64_peak():
+    """measured DFMA issue rate (thread-instructions per second), tools/ubench/fp64_peak.cu -> profiles/r2_fp64_peak.json"""
+    p = os.path.join(ROOT, "profiles", "r2_fp64_peak.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["dfma_peak_tinst_per_s"]), "measured (profiles/r2_fp64_peak.json: DFMA, 32 warps per SM, 8 independent chains)"
+    except Exception:
+        return 148 * 64 * 1.965e9, "nominal (148 SMs x 64 lanes x 1.965 GHz)"
+
+
+# FP64 instructions per unit of the hot kernels, counted in their SASS (profiles/r2_sass_summary.txt): two radix-32 steps
+# (generated codelet, 376 each) + intra-line twiddle chain per pass, + the four-step twiddle in pass 1
+FP64_INST_PER_POINT_FFT = (2 * (2 * 376 + 240) + 265) / 32.0          # 70.3
+FP64_INST_PER_SAMPLE_PWELCH = 734 / 16.0                              # 45.9 (one 4096-point complex transform per 4096 new samples)
+
+
+def cufft_compare(torch, n, batch=256, reps=5):
+    """cuFFT Z2Z through torch.fft.fft on the same kind of batch: a comparison only, never on the product path"""
+    try:
+        x = torch.randn(batch, n, dtype=torch.complex128, device="cuda")
+        torch.fft.fft(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            y = torch.fft.fft(x)
+        e1.record()
+        torch.cuda.synchronize()
+        del y
+        return {"gs_per_s": batch * n * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9, "batch": batch, "api": "torch.fft.fft (cuFFT Z2Z), out of place"}
+    except Exception as ex:
+        return {"unavailable": str(ex)[:100]}
 
 
 class ClockSampler(threading.Thread):
@@ -259,7 +293,10 @@ def run_reference(args):
         "config": {"workload": "batched 2^20-point complex128 FFT (BASELINE.json configs[2]); CPU arm times a bounded sample per step",
                    "n": n, "sample": desc},
         "cpu_baseline": {"value": v, "unit": "GS/s", "cores": threads, "kind": "port",
-                         "sample": desc + "; C restatement of go-dsp (oracle/godsp_oracle.c), not the Go binary (no Go toolchain)"},
+                         "sample": desc + "; C restatement of go-dsp (oracle/godsp_oracle.c), not the Go binary (no Go toolchain)",
+                         "thread_model": "one whole transform per OpenMP thread (every transform is the sequential radix-2 loop of fft/radix2.go); "
+                                         "go-dsp itself runs ONE transform at a time with a goroutine pool and a WaitGroup barrier per stage "
+                                         "(radix2.go:126-151), whose last log2(P) stages under-fill the pool: this arm is kinder to the CPU"},
         "e2e": {"value": v, "unit": "GS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "pwelch": {"metric": "Pwelch Msamples/s", "value": pv, "unit": "Msamples/s",
                    "cpu_baseline": {"value": pv, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": pdesc},
@@ -297,6 +334,7 @@ def run_ours(args):
     sp = C.c_void_p(stream.cuda_stream)
     assert stream.cuda_stream != 0
     hbm_peak, peak_src = peaks()
+    fp64_pk, fp64_src = fp64_peak()
 
     def barrier():
         torch.cuda.synchronize()
@@ -381,13 +419,15 @@ def run_ours(args):
                    "residency": "inputs and outputs resident in HBM (generated on device, SplitMix64 seed 3)",
                    "l2": "inputs (%.1f GiB per GPU) are far larger than L2; no flush needed" % (batch * n * 16 / 2**30),
                    "parallelism": "batch rows sharded over %d GPU(s), no collective" % world},
-        "roofline": {"bound": "hbm", "kernel": "gd::fft_tma_fused2_kernel (both four-step passes of up to 128 transforms per launch; the intermediate stays in L2)",
-                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "peak_source": peak_src, "traffic": ncu_traffic("fft_tma_fused2_kernel"),
-                     "traffic_note": "dram read+write bytes per launch (128 transforms) from profiles/r1_ncu_full_summary.json (ncu --set full): equal to the algorithmic bytes, the inter-pass array never reaches HBM",
+        "roofline": {"bound": "hbm", "kernel": "gd::fft_tma_fused_kernel<false,false> (both four-step passes of up to 512 transforms per launch; the intermediate stays in L2)",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "hbm_frac": achieved / hbm_peak,
+                     "fp64_frac": value / world * 1e9 * FP64_INST_PER_POINT_FFT / fp64_pk, "fp64_peak_tinst_per_s": fp64_pk, "fp64_peak_source": fp64_src,
+                     "fp64_inst_per_point": FP64_INST_PER_POINT_FFT,
+                     "peak_source": peak_src, "traffic": ncu_traffic("fft_tma_fused_kernel"),
+                     "traffic_note": "dram read+write bytes of one launch of 128 transforms (4.29 GB algorithmic) from profiles/r2_ncu_full_summary.json (ncu --set full); the timed launches hold 512 transforms: per-launch traffic scales with the transform count, the inter-pass array never reaches HBM",
                      "algorithmic_bytes_per_launch": per_gpu_bytes / max(1.0, launches_per_step),
                      "avg_launch_us": ms * 1e3 / max(1.0, launches_per_step),
-                     "note": "32 B/point (16 read + 16 written once, SURVEY.md 8d) x points per launch / CUDA-event time per launch; FP64 issue (about 80 FP64 instructions per point) is the co-limiting roof, see DESIGN.md"},
+                     "note": "32 B/point (16 read + 16 written once, SURVEY.md 8d) x points per launch / CUDA-event time per launch; FP64 issue is the co-limiting roof (fp64_frac), and the sustained run sits at the 1000 W power cap (clocks), see DESIGN.md"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
 
@@ -441,6 +481,9 @@ def run_ours(args):
                                 "sample": desc + "; C restatement of go-dsp (oracle/godsp_oracle.c), not the Go binary"}
     del x, y
     torch.cuda.empty_cache()
+    if "cpu" not in skip and world == 1:
+        line["cufft_comparison"] = cufft_compare(torch, n)
+        torch.cuda.empty_cache()
 
     # ---------------- Pwelch
     if "pwelch" not in skip:
@@ -689,9 +732,12 @@ def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_
         "config": {"workload": "spectral.Pwelch, %d float64 samples per GPU, NFFT 4096, Noverlap 2048, Hann (BASELINE.json configs[3])" % ns_local,
                    "samples_per_gpu": ns_local, "segments_total": int(nsegs), "bins": lp,
                    "parallelism": "segment ranges sharded over %d GPU(s); one %d-double all-gather, summed in rank order" % (world, lp)},
-        "roofline": {"bound": "hbm", "kernel": "gd::pwelch_fused_kernel<12>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": ncu_traffic("pwelch_fused_kernel"),
-                     "note": "8 B per input sample (SURVEY.md 8d); FP64 issue rate, not HBM, is the tighter roof for this kernel (DESIGN.md)"},
+        "roofline": {"bound": "hbm", "kernel": "gd::pwelch_bulk_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "hbm_frac": achieved / hbm_peak,
+                     "fp64_frac": value / world * 1e6 * FP64_INST_PER_SAMPLE_PWELCH / fp64_peak()[0], "fp64_inst_per_sample": FP64_INST_PER_SAMPLE_PWELCH,
+                     "peak_source": peak_src, "traffic": ncu_traffic("pwelch_bulk_kernel"),
+                     "traffic_note": "dram bytes of one launch over 2^28 samples (2.15 GB algorithmic) from profiles/r2_ncu_full_summary.json; the timed launch covers 2^30",
+                     "note": "8 B per input sample (SURVEY.md 8d); FP64 issue and the shared-memory pipe, not HBM, are the tighter roofs for this kernel (DESIGN.md 3.4)"},
         "clocks": clocks, "_launches": int(launches), "_parity": par,
         "pxx_checksum": float(pxx.sum().item()),
     }

@@ -287,6 +287,9 @@ int gd_set_option(const char* key, int64_t value) {
     else if (!strcmp(key, "chunk_streams")) { if (value < 1 || value > 4) return (int)invalid_arg("chunk_streams out of range"); d.chunk_streams = (int)value; }
     else if (!strcmp(key, "l2_block_window")) d.l2_block_window = value != 0;
     else if (!strcmp(key, "pwelch_bulk")) d.pwelch_bulk = value != 0;
+    else if (!strcmp(key, "fourstep_pipeline")) d.fourstep_pipeline = value != 0;
+    else if (!strcmp(key, "fourstep_exchange_ctas")) d.fourstep_exchange_ctas = (int)value;
+    else if (!strcmp(key, "fourstep_pipeline_mb")) { if (value < 1) return (int)invalid_arg("fourstep_pipeline_mb < 1"); d.fourstep_pipeline_mb = (int)value; }
     else if (!strcmp(key, "wide_tiles")) d.wide_tiles = value != 0;
     else if (!strcmp(key, "fused")) d.use_fused = value != 0;
     else if (!strcmp(key, "debug_alias")) d.debug_alias = value != 0;
@@ -898,6 +901,13 @@ int gd_fourstep_exchange_dev(const double* slab, void* const* peer_recv, int64_t
     if (!slab || !peer_recv) return (int)invalid_arg("fourstep_exchange_dev: null");
     GD_ENTER();
     return (int)fourstep_exchange((const cpx*)slab, (cpx* const*)peer_recv, n1, w, rank, world, log2n, pick(d, stream));
+}
+int gd_fourstep_lines_exchange_dev(const double* slab, double* tmp, void* const* peer_recv, int64_t n1, int64_t w, int rank, int world,
+                                   int log2n, void* stream) {
+    if (!slab || !tmp || !peer_recv) return (int)invalid_arg("fourstep_lines_exchange_dev: null");
+    GD_ENTER();
+    ScratchOrder order__(d, pick(d, stream));
+    return (int)fourstep_lines_exchange(d, (const cpx*)slab, (cpx*)tmp, (cpx* const*)peer_recv, n1, w, rank, world, log2n, pick(d, stream));
 }
 int gd_peer_block_copy_dev(const double* src, void* const* peers, int world, int rank, int64_t rows, int64_t cols, int64_t src_step,
                            int64_t src_pitch, int64_t dst_off, int64_t dst_pitch, void* stream) {

@@ -86,6 +86,7 @@ Status Device::init(int device) {
         GD_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
     }
     GD_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    GD_CUDA(cudaEventCreateWithFlags(&ev_pipe, cudaEventDisableTiming));
     for (int k = 5; k <= 12; k++) {
         std::vector<cpx> h;
         host_twiddles(h, 1LL << k, 1, 1LL << k);
@@ -122,9 +123,9 @@ void Device::destroy() {
     for (int i = 0; i < SCR_NSLOTS; i++) { if (scratch[i]) cudaFree(scratch[i]); scratch[i] = nullptr; scratch_bytes[i] = 0; }
     cudaStreamDestroy(stream); cudaStreamDestroy(stream_in); cudaStreamDestroy(stream_out);
     for (int i = 0; i < AUX_STREAMS; i++) { cudaStreamDestroy(stream_aux[i]); cudaEventDestroy(ev_join[i]); stream_aux[i] = nullptr; ev_join[i] = nullptr; }
-    cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_fork); cudaEventDestroy(ev_pipe);
     stream = stream_in = stream_out = nullptr;
-    ev_fork = nullptr;
+    ev_fork = ev_pipe = nullptr;
     ready = false;
 }
 
@@ -247,7 +248,8 @@ struct ForkJoin {
 };
 
 // ------------------------------------------------------------------ power-of-two transforms
-static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st);
+static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st,
+                       long long col0 = 0, long long ncols = -1);
 Status transpose_batched(const cpx* in, cpx* out, long long batch, long long rows, long long cols, cudaStream_t st);
 
 // N = 2^25 .. 2^34 on one GPU: an outer four-step over the building blocks below 2^24 (the reference has no length limit,
@@ -541,16 +543,23 @@ Status transpose_batched(const cpx* in, cpx* out, long long batch, long long row
 // already [N2][K], ready for the length-N2 lines.
 struct PeerPtrs { cpx* p[16]; };
 __global__ void __launch_bounds__(256) fourstep_exchange_kernel(const cpx* __restrict__ slab, PeerPtrs peers, long long K,
-                                                                long long W, int g, int log2n, int world_) {
+                                                                long long W, int g, int log2n, int world_, long long cbeg, long long cend,
+                                                                long long nbx, long long nby) {
     __shared__ cpx tile[64][33];
     // consecutive blocks go to different peers, and rank g starts with peer g + 1: with one peer per grid slice every rank
     // wrote to the same destination at the same time (8 GPUs: 56 ms against 34 ms for NCCL's all-to-all)
     const int world = world_;
-    const int h = (int)((blockIdx.x % world + g + 1) % world);
-    const long long k0 = (long long)blockIdx.y * 64, c0 = (long long)(blockIdx.x / world) * 32;
+    // grid-stride over the (x, y) tiles: a pipelined call launches only a few CTAs so that the exchange, which is bound by
+    // NVLink, leaves the SMs to the line kernels it overlaps with
+    const long long ntx = nbx, nty = nby;
+    for (long long t = blockIdx.x; t < ntx * nty; t += gridDim.x) {
+    const long long bxi = t % ntx, byi = t / ntx;
+    __syncthreads();
+    const int h = (int)((bxi % world + g + 1) % world);
+    const long long k0 = byi * 64, c0 = cbeg + (bxi / world) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long long c = c0 + tx;
-    if (c < W) {
+    if (c < cend) {
         const unsigned long long mask = (1ULL << log2n) - 1ULL, n2 = (unsigned long long)g * W + c;
         const double invn = 1.0 / (double)(1ULL << log2n);
         const unsigned long long k1a = (unsigned long long)h * K + k0 + ty;
@@ -569,25 +578,58 @@ __global__ void __launch_bounds__(256) fourstep_exchange_kernel(const cpx* __res
     __syncthreads();
     cpx* dst = peers.p[h] + ((long long)g * W + c0) * K + k0;
     for (int rr = ty; rr < 32; rr += 8) {
-        if (c0 + rr >= W) break;
+        if (c0 + rr >= cend) break;
 #pragma unroll
         for (int kk = tx; kk < 64; kk += 32)
             if (k0 + kk < K) dst[(long long)rr * K + kk] = tile[kk][rr];
     }
+    }
 }
 Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,
-                         cudaStream_t st) {
+                         cudaStream_t st, long long cbeg, long long ccount, int max_ctas) {
     if (!slab || !peer_recv || world < 1 || world > 16 || rank < 0 || rank >= world || n1 % world || w < 1 || log2n < 1 || log2n > 40)
         return invalid("fourstep_exchange: bad arguments");
+    if (ccount < 0) { cbeg = 0; ccount = w; }
+    if (cbeg < 0 || cbeg + ccount > w || ccount < 1) return invalid("fourstep_exchange: bad column range");
     const long long K = n1 / world;
     PeerPtrs pp;
     for (int i = 0; i < 16; i++) pp.p[i] = i < world ? peer_recv[i] : nullptr;
-    const long long gx = (w + 31) / 32, gy = (K + 63) / 64;
-    if (gy > 65535) return invalid("fourstep_exchange: grid too large");
-    // gridDim.z only carries the world size; the peer is picked from blockIdx.x
-    fourstep_exchange_kernel<<<dim3((unsigned)(gx * world), (unsigned)gy, 1), 256, 0, st>>>(slab, pp, K, w, rank, log2n, world);
+    const long long gx = (ccount + 31) / 32, gy = (K + 63) / 64;
+    long long grid = gx * world * gy;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (grid > 2147483647LL) grid = 2147483647LL;
+    fourstep_exchange_kernel<<<(unsigned)grid, 256, 0, st>>>(slab, pp, K, w, rank, log2n, world, cbeg, cbeg + ccount, gx * world, gy);
     g_launches++;
     GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+// First half of the sharded four-step, pipelined: the length-n1 lines of a block of columns (slab -> tmp) run on the
+// caller's stream while the exchange kernel of the previous block (tmp -> peers over NVLink) runs on another one, so the
+// NVLink stores overlap the butterflies instead of following them. The caller fences the ranks before and after.
+Status fourstep_lines_exchange(Device& d, const cpx* slab, cpx* tmp, cpx* const* peer_recv, long long n1, long long w, int rank, int world,
+                               int log2n, cudaStream_t st) {
+    if (!slab || !tmp || slab == tmp) return invalid("fourstep_lines_exchange: bad arguments");
+    const bool blockable = is_pow2(n1) && n1 > 4096 && n1 <= (1LL << 24) && (double)n1 * (double)w < 2147483648.0;
+    long long pb = (long long)(((size_t)d.fourstep_pipeline_mb << 20) / ((size_t)n1 * sizeof(cpx)));   // columns per pipeline block
+    pb = (pb / 32) * 32;
+    if (!d.fourstep_pipeline || !blockable || pb < 32 || w < 2 * pb) {
+        GD_TRY(fft_axis(d, slab, tmp, 1, n1, w, +1, st));
+        return fourstep_exchange(tmp, peer_recv, n1, w, rank, world, log2n, st, 0, -1, 0);
+    }
+    cudaStream_t sx = d.stream_aux[Device::AUX_STREAMS - 1];                          // not one of the chunk streams fft_axis rotates over
+    if (st == sx) return invalid("fourstep_lines_exchange: stream clash");
+    cudaEventRecord(d.ev_fork, st);
+    cudaStreamWaitEvent(sx, d.ev_fork, 0);
+    for (long long c0 = 0; c0 < w; c0 += pb) {
+        const long long nc = w - c0 < pb ? w - c0 : pb;
+        GD_TRY(fft_axis(d, slab, tmp, 1, n1, w, +1, st, c0, nc));
+        GD_CUDA(cudaEventRecord(d.ev_pipe, st));
+        GD_CUDA(cudaStreamWaitEvent(sx, d.ev_pipe, 0));
+        GD_TRY(fourstep_exchange(tmp, peer_recv, n1, w, rank, world, log2n, sx, c0, nc, d.fourstep_exchange_ctas));
+    }
+    GD_CUDA(cudaEventRecord(d.ev_pipe, sx));
+    GD_CUDA(cudaStreamWaitEvent(st, d.ev_pipe, 0));
     return GD_OK;
 }
 
@@ -813,8 +855,11 @@ Status convolve_linear(Device& d, const cpx* x, long long nx, const cpx* h, long
 
 // ------------------------------------------------------------------ N-d transforms
 // one axis: lines (o, i), o < outer, i < s, element stride s, length len. src may equal dst.
-static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st) {
+// col0 / ncols: only columns [col0, col0 + ncols) of every block (power-of-two lengths above 4096 only)
+static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st,
+                       long long col0, long long ncols) {
     const long long nlines = outer * s;
+    const bool sub = ncols >= 0 && !(col0 == 0 && ncols == s);
     if (len == 1) {
         if (src != dst) GD_CUDA(cudaMemcpyAsync(dst, src, (size_t)nlines * sizeof(cpx), cudaMemcpyDeviceToDevice, st));
         return GD_OK;
@@ -831,7 +876,9 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         if (dir < 0) { p.ld_flags = LD_CONJ; p.st_flags = ST_CONJ | ST_SCALE; p.scale = 1.0 / (double)len; }
         return launch_pass(d, l, p, st);
     }
-    if (d.use_tma && d.use_tma14 && tma14_cols_applicable(src, dst, len, s)) {
+    if (sub && !(is_pow2(len) && len > 4096 && len <= (1LL << 24) && (double)len * (double)s < 2147483648.0))
+        return invalid("fft_axis: a column range needs a power-of-two length in (4096, 2^24]");
+    if (!sub && d.use_tma && d.use_tma14 && tma14_cols_applicable(src, dst, len, s)) {
         // every column of a 2^14-row matrix: one fused launch, intermediate resident in L2 (fft_tma14.cuh)
         for (long long o = 0; o < outer; o++)
             GD_TRY(fft_tma_2p14(d, 1, src + o * len * s, 0, dst + o * len * s, 0, s, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
@@ -848,15 +895,16 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         long long cb = (long long)(budget / ((size_t)len * sizeof(cpx)));
         if (cb < 8) cb = 8;
         if (cb > s) cb = s;
-        const long long nblocks = outer * ((s + cb - 1) / cb);
+        const long long cfirst = sub ? col0 : 0, clast = sub ? col0 + ncols : s;
+        const long long nblocks = outer * ((clast - cfirst + cb - 1) / cb);
         ForkJoin fj(d, st, nblocks >= 2 * d.chunk_streams ? d.chunk_streams : 1);
         cpx* scr0;
         GD_TRY(d.ensure_scratch(SCR_PASS, (size_t)fj.ways * len * cb * sizeof(cpx), (void**)&scr0));
         if (nblocks > 1) fj.persist(scr0, (size_t)fj.ways * len * cb * sizeof(cpx));
         long long ci = 0;
         for (long long o = 0; o < outer; o++)
-            for (long long c0 = 0; c0 < s; c0 += cb, ci++) {
-                long long nc = s - c0 < cb ? s - c0 : cb;
+            for (long long c0 = cfirst; c0 < clast; c0 += cb, ci++) {
+                long long nc = clast - c0 < cb ? clast - c0 : cb;
                 cudaStream_t st = fj.stream(ci);
                 cpx* scr = scr0 + (size_t)fj.way(ci) * len * cb;
                 const cpx* sp = src + o * len * s + c0;

@@ -73,7 +73,7 @@ struct Device {
     cudaStream_t stream_out = nullptr;   // D2H
     static constexpr int AUX_STREAMS = 3;
     cudaStream_t stream_aux[AUX_STREAMS] = {nullptr};   // the other L2-sized chunks of a multi-pass transform (ForkJoin, engine.cu)
-    cudaEvent_t ev_fork = nullptr, ev_join[AUX_STREAMS] = {nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_pipe = nullptr, ev_join[AUX_STREAMS] = {nullptr};
     cpx* wl[13] = {nullptr};             // intra-line tables exp(-2 pi i e/L), L = 2^k
     std::map<int, TwiddleTable> tw;      // keyed by log2 M
     std::map<long long, BluesteinPlan> blue;
@@ -81,6 +81,9 @@ struct Device {
     size_t scratch_bytes[SCR_NSLOTS] = {0};
     size_t pass_scratch_budget = 1ull << 30;    // upper bound of the inter-pass scratch of the two-launch four-step path
     size_t l2_block_budget = 24ull << 20;       // inter-pass block of one chunk: small enough to stay in L2 between the passes
+    bool fourstep_pipeline = false;             // sharded four-step: exchange of a column block behind the lines of the next (measured: no gain)
+    int fourstep_pipeline_mb = 256;             // slab bytes per pipeline block
+    int fourstep_exchange_ctas = 0;             // cap on the CTAs of a pipelined exchange launch (0 = one per tile)
     bool pwelch_bulk = true;                    // L = 4096 float64: bulk-copy fed kernel (pwelch.cu)
     int chunk_streams = 2;                      // streams the chunks of one call rotate over (1 .. 1 + AUX_STREAMS)
     bool l2_block_window = true;                // persisting L2 window over the inter-pass blocks of a chunked call
@@ -164,7 +167,9 @@ Status pwelch_finalize(const double* raw, long long lp, long long nsegs, double 
 Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st, int dir = 1);
 Status repack_gkw(const cpx* in, cpx* out, long long G, long long K, long long W, cudaStream_t st);
 Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,
-                         cudaStream_t st);
+                         cudaStream_t st, long long cbeg = 0, long long ccount = -1, int max_ctas = 0);
+Status fourstep_lines_exchange(Device& d, const cpx* slab, cpx* tmp, cpx* const* peer_recv, long long n1, long long w, int rank, int world,
+                               int log2n, cudaStream_t st);
 Status peer_block_copy(const cpx* src, cpx* const* peers, int world, int rank, long long rows, long long cols, long long src_step,
                        long long src_pitch, long long dst_off, long long dst_pitch, cudaStream_t st);
 Status transpose_batched(const cpx* in, cpx* out, long long batch, long long rows, long long cols, cudaStream_t st);

@@ -115,6 +115,11 @@ class PeerExchange:
     def exchange(self, slab, n1, w, log2n):
         _capi.check(self.L.gd_fourstep_exchange_dev(slab.data_ptr(), self.ptr_array, n1, w, self.rank, self.world, log2n, self.ops._sp()))
 
+    def lines_exchange(self, slab, tmp, n1, w, log2n):
+        """length-n1 lines of the slab into `tmp`, pipelined with the exchange of the finished column blocks"""
+        _capi.check(self.L.gd_fourstep_lines_exchange_dev(slab.data_ptr(), tmp.data_ptr(), self.ptr_array, n1, w, self.rank, self.world, log2n,
+                                                          self.ops._sp()))
+
     def block_copy(self, src, rows, cols, src_step, src_pitch, dst_off, dst_pitch):
         """every peer h: peer_buffer[h][dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c]"""
         _capi.check(self.L.gd_peer_block_copy_dev(src.data_ptr(), self.ptr_array, self.world, self.rank, rows, cols, src_step, src_pitch,
@@ -158,9 +163,10 @@ def fft_1d_sharded(slab, n, ops, group=None, work=None, peer=None):
         raise ValueError("slab has %d elements, expected %d" % (slab.numel(), n1 * w))
     if peer is not None:
         out = work if work is not None else ops.empty(n1 * w)
-        ops.fft_strided(slab, out, 1, n1, w, 1)           # lines over n1, into `out` (the slab is left untouched)
         peer.fence()                                      # every rank is done reading its receive buffer (previous call)
-        peer.exchange(out, n1, w, _ilog2(n))              # peer h gets [rank*W + c][k] <- out[h*K + k][c] * w_N^(k1 n2)
+        # lines over n1 into `out` (the slab is left untouched) and, block of columns by block of columns behind them, the
+        # exchange: peer h gets [rank*W + c][k] <- out[h*K + k][c] * w_N^(k1 n2)
+        peer.lines_exchange(slab, out, n1, w, _ilog2(n))
         peer.fence()                                      # every rank's stores have landed
         ops.fft_strided(peer.recv, out, 1, n2, k, 1)      # lines over n2
         return out

@@ -152,6 +152,10 @@ GD_API int gd_transpose_batched_dev(const double* in_dev, double* out_dev, int64
  * ranks around it (a stream-ordered collective before and after). */
 GD_API int gd_fourstep_exchange_dev(const double* slab_dev, void* const* peer_recv, int64_t n1, int64_t w, int rank, int world,
                                     int log2n, void* stream);
+/* The length-n1 lines of the slab (slab -> tmp, both [n1][w]) and the exchange above, pipelined over blocks of columns:
+ * the NVLink stores of one block overlap the butterflies of the next. Same rendezvous rules as gd_fourstep_exchange_dev. */
+GD_API int gd_fourstep_lines_exchange_dev(const double* slab_dev, double* tmp_dev, void* const* peer_recv, int64_t n1, int64_t w, int rank,
+                                          int world, int log2n, void* stream);
 /* FFT2 on row blocks: an exchange as strided block copies into peer memory; for every peer h (complex128 elements):
  * peers[h][dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c], r < rows, c < cols */
 GD_API int gd_peer_block_copy_dev(const double* src_dev, void* const* peers, int world, int rank, int64_t rows, int64_t cols, int64_t src_step,
