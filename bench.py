@@ -92,16 +92,48 @@ FP64_INST_PER_POINT_FFT = (2 * (2 * 376 + 240) + 265) / 32.0          # 70.3
 FP64_INST_PER_SAMPLE_PWELCH = 734 / 16.0                              # 45.9 (one 4096-point complex transform per 4096 new samples)
 
 
+def pcie_ceiling(torch, dist, world, barrier, nbytes):
+    """What the box's PCIe / host memory gives when every rank copies nbytes up and nbytes down AT THE SAME TIME (pinned
+    memory, two streams, no kernels): the ceiling of the end-to-end numbers at this GPU count."""
+    try:
+        hp, hq = torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dp, dq = torch.empty(nbytes, dtype=torch.uint8, device="cuda"), torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def both():
+            with torch.cuda.stream(s1):
+                dp.copy_(hp, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hq.copy_(dq, non_blocking=True)
+            s1.synchronize(); s2.synchronize()
+        both()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            both()
+        dt = (time.perf_counter() - t0) / 3
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return {"each_way_gbs_per_gpu": nbytes / dt / 1e9, "each_way_gbs_aggregate": world * nbytes / dt / 1e9,
+                "e2e_gs_per_s_at_this_ceiling": world * nbytes / dt / 1e9 / 16.0,
+                "how": "every rank copies %d MiB host->device and device->host concurrently from torch-pinned memory, max over ranks" % (nbytes >> 20)}
+    except Exception as ex:
+        return {"unavailable": str(ex)[:120]}
+
+
 def cufft_compare(torch, n, batch=256, reps=5):
     """cuFFT Z2Z through torch.fft.fft on the same kind of batch: a comparison only, never on the product path"""
     try:
         x = torch.randn(batch, n, dtype=torch.complex128, device="cuda")
-        torch.fft.fft(x)
+        y = torch.empty_like(x)
+        torch.fft.fft(x, out=y)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            y = torch.fft.fft(x)
+            torch.fft.fft(x, out=y)
         e1.record()
         torch.cuda.synchronize()
         del y
@@ -446,6 +478,7 @@ def run_ours(args):
             capi.check(L.gd_fft_batch_c2c(hin, hout, n, eb, 1))
 
         ems = timed_host(e2e_step, args.e2e_steps, 1)
+        line["e2e_pcie_ceiling"] = pcie_ceiling(torch, dist, world, barrier, min(nbytes, 1 << 30))
         line["e2e"] = {"value": eb * n * world / (ems * 1e-3) / 1e9, "unit": "GS/s", "h2d_bytes_per_step": nbytes,
                        "d2h_bytes_per_step": nbytes, "ms_per_step": ems, "batch_per_gpu": eb,
                        "api": "gd_fft_batch_c2c (pinned host in/out; chunked H2D / kernels / D2H overlap on 3 streams)"}
@@ -759,6 +792,40 @@ def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_
                       "d2h_bytes_per_step": lp * 8, "ms_per_step": ems,
                       "api": "gd_pwelch_f64 (pinned host signal streamed in 256 MiB ranges, H2D overlapped with the fused kernel)"}
         L.gd_pinned_free(hx)
+        # the same PSD from 16-bit PCM as wav.ReadSamples returns it: the ReadFloats conversion (wav/wav.go:138-161) runs in the
+        # kernel's segment load, so the signal crosses PCIe at 2 bytes per sample instead of 8
+        hx16 = L.gd_pinned_alloc(nloc * 2)
+        if hx16:
+            pcm = np.ctypeslib.as_array((C.c_int16 * nloc).from_address(hx16))
+            blk = 1 << 24                                  # deterministic 16-bit signal: one hashed block, re-keyed per block and rank
+            i = np.arange(blk, dtype=np.int64)
+            base = (((i * 2654435761) >> 7) & 0xFFFF).astype(np.uint16).view(np.int16)
+            for k, a in enumerate(range(0, nloc, blk)):
+                e = min(nloc, a + blk)
+                pcm[a:e] = base[: e - a] ^ np.int16(((k + 1 + 64 * rank) * 7919) & 0x7FFF)
+            del i, base
+            hp16 = np.empty(lp)
+
+            def e2e16_step():
+                capi.check(L.gd_pwelch_samples(hx16, 2, nloc, nfft, nov, nfft, lp, nseg_loc, win.ctypes.data, norm, hp16.ctypes.data))
+
+            ems16 = timed_host(e2e16_step, args.e2e_steps, 1)
+            # parity of the PCM path: a 2^22-sample prefix against oracle.pwelch of the oracle's ReadFloats restatement
+            import oracle
+            npre = min(1 << 22, nloc)
+            nsp = (npre - nfft) // stride + 1
+            hpre = np.empty(lp)
+            capi.check(L.gd_pwelch_samples(hx16, 2, npre, nfft, nov, nfft, lp, nsp, win.ctypes.data, norm, hpre.ctypes.data))
+            xf = oracle.wav_read_floats(pcm[:npre].astype("<i2").tobytes(), 2, npre).astype(np.float64)
+            want16, _ = oracle.pwelch(xf, 1.0, nfft=nfft, noverlap=nov, threads=min(8, os.cpu_count() or 1))
+            e16 = rel_l2(hpre, want16)
+            out["e2e_pcm16"] = {"value": total / (ems16 * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": nloc * 2,
+                                "d2h_bytes_per_step": lp * 8, "ms_per_step": ems16, "prefix_rel_l2_vs_oracle": e16,
+                                "api": "gd_pwelch_samples(GD_SAMPLE_S16): int16 PCM over PCIe, decoded in the Pwelch kernel's segment load"}
+            out["_parity"]["max_rel_l2"] = allmax(torch, dist, world, max(out["_parity"]["max_rel_l2"], e16))
+            out["_parity"]["pcm16_prefix_rel_l2"] = e16
+            del pcm
+            L.gd_pinned_free(hx16)
     if "cpu" not in skip and world == 1:
         threads = os.cpu_count() or 1
         v, desc, _ = cpu_pwelch_sample(threads, 1.5)

@@ -541,8 +541,8 @@ Status transpose_batched(const cpx* in, cpx* out, long long batch, long long row
 // through shared memory and stores it straight into rank h's receive buffer at [g*W + c][k] (rows of K elements,
 // 1 KiB contiguous per row segment). One HBM read + one NVLink write per element; the receive buffer is then
 // already [N2][K], ready for the length-N2 lines.
-struct PeerPtrs { cpx* p[16]; };
-__global__ void __launch_bounds__(256) fourstep_exchange_kernel(const cpx* __restrict__ slab, PeerPtrs peers, long long K,
+struct PeerPtrs { cpx* p[16]; };      // passed as __grid_constant__: indexed in the parameter bank, no local-memory copy
+__global__ void __launch_bounds__(256) fourstep_exchange_kernel(const cpx* __restrict__ slab, const __grid_constant__ PeerPtrs peers, long long K,
                                                                 long long W, int g, int log2n, int world_, long long cbeg, long long cend,
                                                                 long long nbx, long long nby) {
     __shared__ cpx tile[64][33];
@@ -635,7 +635,7 @@ Status fourstep_lines_exchange(Device& d, const cpx* slab, cpx* tmp, cpx* const*
 
 // FFT2 on row blocks: both exchanges are strided block copies into peer memory (no repack kernels, no NCCL data
 // movement). For every peer h: dst_h[dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c], r < rows, c < cols.
-__global__ void __launch_bounds__(256) peer_block_copy_kernel(const cpx* __restrict__ src, PeerPtrs peers, long long rows, long long cols,
+__global__ void __launch_bounds__(256) peer_block_copy_kernel(const cpx* __restrict__ src, const __grid_constant__ PeerPtrs peers, long long rows, long long cols,
                                                               long long src_step, long long src_pitch, long long dst_off, long long dst_pitch,
                                                               int world, int rank) {
     const int h = (int)((blockIdx.x % world + rank + 1) % world);      // consecutive blocks -> different peers, rotated by rank

@@ -17,10 +17,6 @@ def sync(): capi.check(L.gd_stream_sync(None)); torch.cuda.synchronize()
 n, b = 1 << 20, 128
 x, y = dev(n * b), dev(n * b); fill(x, 3); sync()
 capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, b, 1, None)); sync()
-# 2. 32-point-per-thread pass kernel (the two-launch schedule of the same size, 16 transforms)
-capi.check(L.gd_set_option(b"tma", 0))
-capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, 16, 1, None)); sync()
-capi.check(L.gd_set_option(b"tma", 1))
 del x, y
 # 3. fused 2^14 kernel: columns of a 16384 x 2048 matrix, rows of a 2048 x 16384 matrix
 m, o = dev(16384 * 2048), dev(16384 * 2048); fill(m, 4); sync()
@@ -38,8 +34,14 @@ raw = torch.empty(nfft // 2 + 1, dtype=torch.float64, device="cuda")
 sync()
 capi.check(L.gd_pwelch_partial_dev(s.data_ptr(), nfft, nov, nfft, nfft // 2 + 1, 0, (ns - nfft) // (nfft - nov) + 1, dwin.data_ptr(), raw.data_ptr(), None)); sync()
 del s
+# 2. 32-point-per-thread pass kernel (the two-launch schedule of the same size, one transform)
+capi.check(L.gd_set_option(b"tma", 0))
+x2, y2 = dev(n), dev(n); fill(x2, 3); sync()
+capi.check(L.gd_fft_batch_c2c_dev(x2.data_ptr(), y2.data_ptr(), n, 1, 1, None)); sync()
+del x2, y2
+capi.check(L.gd_set_option(b"tma", 1))
 # 6. Bluestein, N = 1,000,003 (GENERIC passes with fused chirp / product / truncation), batch 8
-nb, bb = 1000003, 2
+nb, bb = 1000003, 1
 xb, yb = dev(nb * bb), dev(nb * bb); fill(xb, 2); sync()
 capi.check(L.gd_fft_batch_c2c_dev(xb.data_ptr(), yb.data_ptr(), nb, bb, 1, None)); sync()
 del xb, yb
