@@ -20,7 +20,13 @@ using namespace gd;
 namespace {
 
 constexpr int kMaxDev = 16;
-Device g_dev[kMaxDev];
+// Lanes: independent execution contexts of one GPU (own streams, events, scratch, staging, plan caches). A call takes a free
+// lane of its device, so concurrent host threads (goroutines) working on the same GPU overlap their copies and kernels
+// instead of queueing on one mutex; a single-threaded caller always gets lane 0.
+constexpr int kLanes = 2;
+Device g_dev[kMaxDev * kLanes];
+inline Device& lane_of(int dev, int lane) { return g_dev[dev * kLanes + lane]; }
+thread_local int t_lane_held[kMaxDev] = {0};            // 1 + lane this thread currently holds on a device (nested entry points)
 std::atomic<int> g_ndev{0};
 std::mutex g_init_mu;
 thread_local int t_dev = 0;
@@ -29,10 +35,10 @@ struct StageEvents {
     cudaEvent_t h2d[2] = {nullptr, nullptr}, comp[2] = {nullptr, nullptr}, d2h[2] = {nullptr, nullptr};
     bool ready = false;
 };
-StageEvents g_ev[kMaxDev];
+StageEvents g_ev[kMaxDev * kLanes];
 
-Status ensure_events(int dev) {
-    StageEvents& e = g_ev[dev];
+Status ensure_events(int slot) {
+    StageEvents& e = g_ev[slot];
     if (e.ready) return ::gd::GD_OK;
     for (int i = 0; i < 2; i++) {
         GD_CUDA(cudaEventCreateWithFlags(&e.h2d[i], cudaEventDisableTiming));
@@ -57,7 +63,7 @@ Status ensure_device(int dev) {
         g_ndev.store(have > kMaxDev ? kMaxDev : have);
     }
     if (dev < 0 || dev >= g_ndev.load()) { set_error("device index out of range"); return ::gd::GD_ERR_INVALID; }
-    if (!g_dev[dev].ready) GD_TRY(g_dev[dev].init(dev));
+    if (!lane_of(dev, 0).ready) GD_TRY(lane_of(dev, 0).init(dev, 0));
     return ::gd::GD_OK;
 }
 
@@ -66,14 +72,35 @@ struct DevLock {
     Device* d = nullptr;
     Status st = ::gd::GD_OK;
     std::unique_lock<std::recursive_mutex> lk;
-    DevLock() {
-        st = ensure_device(t_dev);
+    int dev = 0, prev_held = 0;
+    explicit DevLock(int only_lane = -1) {
+        dev = t_dev;
+        st = ensure_device(dev);
         if (st != ::gd::GD_OK) return;
-        d = &g_dev[t_dev];
-        lk = std::unique_lock<std::recursive_mutex>(d->mu);
+        prev_held = t_lane_held[dev];
+        if (only_lane >= 0) {                               // gd_set_option walks every lane
+            d = &lane_of(dev, only_lane);
+            lk = std::unique_lock<std::recursive_mutex>(d->mu);
+        } else if (prev_held) {                             // nested entry point: stay on the lane this thread already holds
+            d = &lane_of(dev, prev_held - 1);
+            lk = std::unique_lock<std::recursive_mutex>(d->mu);
+        } else {
+            for (int k = 0; k < kLanes && !d; k++) {
+                std::unique_lock<std::recursive_mutex> l(lane_of(dev, k).mu, std::try_to_lock);
+                if (l.owns_lock()) { d = &lane_of(dev, k); lk = std::move(l); }
+            }
+            if (!d) {                                       // all busy: queue on one of them
+                d = &lane_of(dev, (int)(std::hash<std::thread::id>()(std::this_thread::get_id()) % kLanes));
+                lk = std::unique_lock<std::recursive_mutex>(d->mu);
+            }
+        }
+        const int lane = (int)(d - &lane_of(dev, 0));
+        t_lane_held[dev] = 1 + lane;
+        if (!d->ready) { st = d->init(dev, lane); if (st != ::gd::GD_OK) return; }
         cudaError_t e = cudaSetDevice(d->dev);
         if (e != cudaSuccess) st = cuda_fail(e, "cudaSetDevice");
     }
+    ~DevLock() { if (lk.owns_lock()) t_lane_held[dev] = prev_held; }
 };
 
 #define GD_ENTER()        \
@@ -210,9 +237,9 @@ struct PinnedRing {              // per device: two input and two output slots, 
     char* out[2] = {nullptr, nullptr};
     size_t in_bytes = 0, out_bytes = 0;
 };
-PinnedRing g_ring[kMaxDev];
-Status ensure_ring(int dev, size_t in_bytes, size_t out_bytes) {
-    PinnedRing& r = g_ring[dev];
+PinnedRing g_ring[kMaxDev * kLanes];
+Status ensure_ring(int slot, int dev, size_t in_bytes, size_t out_bytes) {
+    PinnedRing& r = g_ring[slot];
     NearDevice near(dev);
     if (r.in_bytes < in_bytes) {
         for (int i = 0; i < 2; i++) { if (r.in[i]) cudaFreeHost(r.in[i]); r.in[i] = nullptr; }
@@ -250,7 +277,7 @@ int gd_init(int ndev) {
 int gd_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_init_mu);
     g_fanout.store(1);
-    for (int i = 0; i < g_ndev.load(); i++) {
+    for (int i = 0; i < g_ndev.load() * kLanes; i++) {
         PinnedRing& r = g_ring[i];
         for (int k = 0; k < 2; k++) { if (r.in[k]) cudaFreeHost(r.in[k]); if (r.out[k]) cudaFreeHost(r.out[k]); r.in[k] = r.out[k] = nullptr; }
         r.in_bytes = r.out_bytes = 0;
@@ -269,7 +296,7 @@ const char* gd_last_error(void) { return last_error(); }
 
 int gd_device_count(void) {
     int n = 0;
-    for (int i = 0; i < g_ndev.load(); i++) n += g_dev[i].ready ? 1 : 0;
+    for (int i = 0; i < g_ndev.load(); i++) n += lane_of(i, 0).ready ? 1 : 0;
     return n;
 }
 
@@ -280,12 +307,22 @@ int gd_use_device(int dev) {
     return ::gd::GD_OK;
 }
 
+static int set_option_one(Device& d, const char* key, int64_t value);
 int gd_set_option(const char* key, int64_t value) {
-    GD_ENTER();
+    if (!key) return (int)invalid_arg("gd_set_option: null key");
+    for (int k = 0; k < kLanes; k++) {                      // every lane of the calling thread's device gets the value
+        DevLock L__(k);
+        if (L__.st != ::gd::GD_OK) return (int)L__.st;
+        const int rc = set_option_one(*L__.d, key, value);
+        if (rc) return rc;
+    }
+    return ::gd::GD_OK;
+}
+static int set_option_one(Device& d, const char* key, int64_t value) {
     if (!strcmp(key, "pass_scratch_mb")) { if (value < 1) return (int)invalid_arg("pass_scratch_mb < 1"); d.pass_scratch_budget = (size_t)value << 20; }
     else if (!strcmp(key, "l2_block_mb")) { if (value < 1) return (int)invalid_arg("l2_block_mb < 1"); d.l2_block_budget = (size_t)value << 20; }
     else if (!strcmp(key, "chunk_streams")) { if (value < 1 || value > 4) return (int)invalid_arg("chunk_streams out of range"); d.chunk_streams = (int)value; }
-    else if (!strcmp(key, "l2_block_window")) d.l2_block_window = value != 0;
+    else if (!strcmp(key, "l2_block_window")) d.l2_block_window = value != 0 && d.lane == 0;
     else if (!strcmp(key, "pwelch_bulk")) d.pwelch_bulk = value != 0;
     else if (!strcmp(key, "fourstep_pipeline")) d.fourstep_pipeline = value != 0;
     else if (!strcmp(key, "fourstep_exchange_ctas")) d.fourstep_exchange_ctas = (int)value;
@@ -301,7 +338,7 @@ int gd_set_option(const char* key, int64_t value) {
     else if (!strcmp(key, "tma_delay")) { if (value < 0 || value > 4) return (int)invalid_arg("tma_delay out of range"); d.tma_delay = (int)value; }
     else if (!strcmp(key, "tma_slots")) { if (value < 2 || value > 6) return (int)invalid_arg("tma_slots out of range"); d.tma_slots = (int)value; }
     else if (!strcmp(key, "tiled_scratch")) d.tiled_scratch = value != 0;
-    else if (!strcmp(key, "l2_window")) d.use_l2_window = value != 0;
+    else if (!strcmp(key, "l2_window")) d.use_l2_window = value != 0 && d.lane == 0;
     else if (!strcmp(key, "fused_delay")) { if (value < 1 || value > 6) return (int)invalid_arg("fused_delay out of range"); d.fused_delay = (int)value; }
     else if (!strcmp(key, "fused_slot_mb")) { if (value < 1) return (int)invalid_arg("fused_slot_mb < 1"); d.fused_slot_budget = (size_t)value << 20; }
     else return (int)invalid_arg("gd_set_option: unknown key");
@@ -343,8 +380,8 @@ static int fft_host(const double* in, double* out, int64_t n, int64_t batch, boo
     }
     GD_ENTER();
     ScratchOrder order__(d, d.stream);
-    GD_TRY(ensure_events(d.dev));
-    StageEvents& ev = g_ev[d.dev];
+    GD_TRY(ensure_events(d.slot()));
+    StageEvents& ev = g_ev[d.slot()];
     const size_t in_el = real_in ? sizeof(double) : sizeof(cpx);
     // chunk the batch so H2D of chunk c+1, the kernels of chunk c and D2H of chunk c-1 overlap
     long long chunk = (long long)((128ull << 20) / ((size_t)n * sizeof(cpx)));
@@ -368,8 +405,8 @@ static int fft_host(const double* in, double* out, int64_t n, int64_t batch, boo
         // pageable memory: every chunk goes through the pinned ring, filled / drained by host threads while the copy
         // engines and the kernels work on the neighbouring chunks
         const size_t cin = (size_t)chunk * n * in_el, cout = (size_t)chunk * n * sizeof(cpx);
-        GD_TRY(ensure_ring(d.dev, cin, cout));
-        PinnedRing& ring = g_ring[d.dev];
+        GD_TRY(ensure_ring(d.slot(), d.dev, cin, cout));
+        PinnedRing& ring = g_ring[d.slot()];
         const long long nchunks = (batch + chunk - 1) / chunk;
         std::thread drain;
         cudaError_t drain_err = cudaSuccess;
@@ -546,8 +583,8 @@ static int pwelch_samples_one(const void* xv, int sample_fmt, int64_t nfft, int6
     const char* x = (const char*)xv;
     GD_ENTER();
     ScratchOrder order__(d, d.stream);
-    GD_TRY(ensure_events(d.dev));
-    StageEvents& ev = g_ev[d.dev];
+    GD_TRY(ensure_events(d.slot()));
+    StageEvents& ev = g_ev[d.slot()];
     // stream the signal through two device buffers, a range of whole segments at a time; PCM formats travel as they are on
     // disk (1, 2 or 4 bytes per sample) and are decoded by the segment load of the kernel
     long long segs_per_chunk = std::max<long long>(1, (long long)(((256ull << 20) / ssz - (size_t)nfft) / (size_t)stride));

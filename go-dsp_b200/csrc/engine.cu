@@ -63,10 +63,11 @@ static Status upload(const std::vector<cpx>& h, cpx** dptr) {
     return GD_OK;
 }
 
-Status Device::init(int device) {
+Status Device::init(int device, int lane_index) {
     std::lock_guard<std::recursive_mutex> lk(mu);
     if (ready) return GD_OK;
     dev = device;
+    lane = lane_index;
     GD_CUDA(cudaSetDevice(dev));
     cudaDeviceProp prop;
     GD_CUDA(cudaGetDeviceProperties(&prop, dev));
@@ -104,6 +105,9 @@ Status Device::init(int device) {
     if (const char* s = getenv("GD_TMA")) use_tma = atoi(s) != 0;
     if (const char* s = getenv("GD_L2_WINDOW")) use_l2_window = atoi(s) != 0;
     if (const char* s = getenv("GD_FUSED_DELAY")) { int v = atoi(s); if (v >= 1 && v <= 6) fused_delay = v; }
+    // the persisting L2 set-aside is one per GPU: only lane 0 carves and resets it (the other lanes' fused kernels run
+    // without the window, with the evict-last hints alone)
+    if (lane != 0) { use_l2_window = false; l2_block_window = false; }
     if (getenv("GD_VERBOSE")) fprintf(stderr, "[godsp] dev %d: %d SMs, L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", dev, num_sms, prop.l2CacheSize >> 20, l2_persist_max >> 20, l2_window_max >> 20);
     ready = true;
     return GD_OK;

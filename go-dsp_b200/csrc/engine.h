@@ -66,6 +66,8 @@ enum ScratchSlot { SCR_PASS = 0, SCR_A, SCR_B, SCR_C, SCR_STAGE_IN, SCR_STAGE_OU
 
 struct Device {
     int dev = -1;
+    int lane = 0;                        // execution lane of the device this object is (capi.cu); lane 0 owns the persisting L2 window
+    int slot() const { return dev * 2 + lane; }
     int num_sms = 0;
     bool ready = false;
     cudaStream_t stream = nullptr;       // compute stream of the host-pointer entry points
@@ -113,7 +115,7 @@ struct Device {
     bool scratch_used = false;
     std::recursive_mutex mu;             // every public entry point locks its device
 
-    Status init(int device);
+    Status init(int device, int lane_index = 0);
     void destroy();
     Status ensure_scratch(ScratchSlot s, size_t bytes, void** out);
     // give the whole L2 back to kernels that do not use the persisting window (called lazily by their launchers)

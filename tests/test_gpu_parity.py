@@ -454,3 +454,47 @@ def test_two_streams_share_the_device_scratch(gd):
         assert float(((ey / n - ex).abs() / ex).max()) < 1e-13
         row = x.view(b, -1)[b - 1].cpu().numpy().view(np.complex128)
         assert rel_l2(y.view(b, -1)[b - 1].cpu().numpy().view(np.complex128), oracle.fft(row)) <= TOL
+
+
+def test_concurrent_callers_one_device(gd):      # goroutines calling into one GPU: lanes (own streams / scratch / staging) instead of one mutex
+    import threading
+    _, capi, L = gd
+    jobs = [(1 << 20, 4, 3), (1 << 14, 128, 5), (4096, 300, 7), (1000003, 1, 9), (1 << 16, 16, 11), (1 << 20, 3, 13)]
+    res, errs = {}, []
+
+    def work(i, n, b, seed):
+        try:
+            capi.check(L.gd_use_device(0))
+            x = oracle.splitmix_complex(n * b, seed).reshape(b, n)
+            out = np.empty_like(x)
+            for _ in range(3):
+                capi.check(L.gd_fft_batch_c2c(x.ctypes.data, out.ctypes.data, n, b, 1))
+            res[i] = (x, out)
+        except Exception as e:                     # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,) + j) for i, j in enumerate(jobs)]
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join(timeout=300)
+    assert not errs, errs
+    assert len(res) == len(jobs)
+    for i, (n, b, seed) in enumerate(jobs):
+        x, out = res[i]
+        assert rel_l2(out, oracle.fft_batch(x, threads=8)) <= TOL, (n, b)
+    # Pwelch and FFT2 from two threads at once
+    sig = oracle.fill_splitmix(1 << 22, 5)
+    godsp = gd[0]
+    outp = {}
+
+    def pw(k):
+        outp[k] = godsp.spectral.Pwelch(sig, 1.0, godsp.spectral.PwelchOptions(NFFT=4096, Noverlap=2048))[0]
+    th = [threading.Thread(target=pw, args=(k,)) for k in range(3)]
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join(timeout=300)
+    want, _ = oracle.pwelch(sig, 1.0, nfft=4096, noverlap=2048, threads=8)
+    for k in range(3):
+        assert rel_l2(outp[k], want) <= TOL
