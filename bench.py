@@ -455,8 +455,10 @@ def run_ours(args):
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "hbm_frac": achieved / hbm_peak,
                      "fp64_frac": value / world * 1e9 * FP64_INST_PER_POINT_FFT / fp64_pk, "fp64_peak_tinst_per_s": fp64_pk, "fp64_peak_source": fp64_src,
                      "fp64_inst_per_point": FP64_INST_PER_POINT_FFT,
-                     "peak_source": peak_src, "traffic": ncu_traffic("fft_tma_fused_kernel"),
-                     "traffic_note": "dram read+write bytes of one launch of 128 transforms (4.29 GB algorithmic) from profiles/r2_ncu_full_summary.json (ncu --set full); the timed launches hold 512 transforms: per-launch traffic scales with the transform count, the inter-pass array never reaches HBM",
+                     "peak_source": peak_src,
+                     "traffic": (ncu_traffic("fft_tma_fused_kernel") or 0) * (batch / max(1.0, launches_per_step)) / 128.0 or None,
+                     "traffic_profiled_launch": ncu_traffic("fft_tma_fused_kernel"),
+                     "traffic_note": "profiles/r2_ncu_full_summary.json (ncu --set full) holds one launch of 128 transforms: 4.27 GB of dram read+write against 4.29 GB algorithmic; `traffic` scales that to the transforms per timed launch (the inter-pass array never reaches HBM, so traffic is proportional to the transform count)",
                      "algorithmic_bytes_per_launch": per_gpu_bytes / max(1.0, launches_per_step),
                      "avg_launch_us": ms * 1e3 / max(1.0, launches_per_step),
                      "note": "32 B/point (16 read + 16 written once, SURVEY.md 8d) x points per launch / CUDA-event time per launch; FP64 issue is the co-limiting roof (fp64_frac), and the sustained run sits at the 1000 W power cap (clocks), see DESIGN.md"},
@@ -768,8 +770,9 @@ def run_pwelch(args, torch, dist, capi, L, sp, world, rank, local, timed, timed_
         "roofline": {"bound": "hbm", "kernel": "gd::pwelch_bulk_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "hbm_frac": achieved / hbm_peak,
                      "fp64_frac": value / world * 1e6 * FP64_INST_PER_SAMPLE_PWELCH / fp64_peak()[0], "fp64_inst_per_sample": FP64_INST_PER_SAMPLE_PWELCH,
-                     "peak_source": peak_src, "traffic": ncu_traffic("pwelch_bulk_kernel"),
-                     "traffic_note": "dram bytes of one launch over 2^28 samples (2.15 GB algorithmic) from profiles/r2_ncu_full_summary.json; the timed launch covers 2^30",
+                     "peak_source": peak_src, "traffic": (ncu_traffic("pwelch_bulk_kernel") or 0) * (ns_local / float(1 << 28)) or None,
+                     "traffic_profiled_launch": ncu_traffic("pwelch_bulk_kernel"),
+                     "traffic_note": "profiles/r2_ncu_full_summary.json holds one launch over 2^28 samples: 2.15 GB of dram traffic = the algorithmic 8 B per sample; `traffic` scales that to the samples of the timed launch",
                      "note": "8 B per input sample (SURVEY.md 8d); FP64 issue and the shared-memory pipe, not HBM, are the tighter roofs for this kernel (DESIGN.md 3.4)"},
         "clocks": clocks, "_launches": int(launches), "_parity": par,
         "pxx_checksum": float(pxx.sum().item()),

@@ -52,6 +52,14 @@ class DeviceOps:
         # own stream", which would not be ordered with the collectives, so name the legacy stream explicitly
         return C.c_void_p(s.cuda_stream if s.cuda_stream else 1)          # 1 = cudaStreamLegacy
 
+    def stream_context(self):
+        """context under which torch collectives are ordered with this object's kernels (no-op when they already run on
+        torch's current stream)"""
+        import contextlib
+        if self.stream is None or self.stream == torch.cuda.current_stream(self.device):
+            return contextlib.nullcontext()
+        return torch.cuda.stream(self.stream)
+
     def empty(self, nelem):
         return torch.empty(nelem, dtype=torch.complex128, device=self.device)
 
@@ -109,8 +117,10 @@ class PeerExchange:
 
     def fence(self):
         """stream-ordered rendezvous of all ranks (a 1-element all-reduce): nobody passes before everybody's kernels
-        enqueued so far are done"""
-        dist.all_reduce(self.token, group=self.group)
+        enqueued so far are done. torch.distributed orders a collective against torch's CURRENT stream, so it is issued
+        under the stream the kernels of `ops` run on."""
+        with self.ops.stream_context():
+            dist.all_reduce(self.token, group=self.group)
 
     def exchange(self, slab, n1, w, log2n):
         _capi.check(self.L.gd_fourstep_exchange_dev(slab.data_ptr(), self.ptr_array, n1, w, self.rank, self.world, log2n, self.ops._sp()))
@@ -136,9 +146,12 @@ class PeerExchange:
         _capi.check(self.L.gd_dev_free(self.own))
 
 
-def _all_to_all(recv, send, group):
-    # equal contiguous splits; complex128 travels as pairs of float64
-    dist.all_to_all_single(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), group=group)
+def _all_to_all(recv, send, group, ops=None):
+    # equal contiguous splits; complex128 travels as pairs of float64; issued under the stream of `ops` (see PeerExchange.fence)
+    import contextlib
+    ctx = ops.stream_context() if ops is not None and hasattr(ops, "stream_context") else contextlib.nullcontext()
+    with ctx:
+        dist.all_to_all_single(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), group=group)
 
 
 def split_1d(n, world):
@@ -176,7 +189,7 @@ def fft_1d_sharded(slab, n, ops, group=None, work=None, peer=None):
     # 2. slab[k1][c] *= w_N^(k1 * (rank*W + c))
     ops.fourstep_twiddle(slab, n1, w, 0, rank * w, _ilog2(n))
     # 3. rows [h*K, (h+1)*K) go to rank h; received: [source g][K][W]
-    _all_to_all(recv, slab, group)
+    _all_to_all(recv, slab, group, ops)
     # 4. per source [K][W] -> [W][K]: the buffer becomes [N2][K] (n2 = g*W + c)
     ops.transpose_batched(recv, slab, world, k, w)
     # 5. lines over n2 (length N2, element stride K): out[k2][k1_local]
@@ -223,9 +236,9 @@ def fft2_sharded(block, rows, cols, ops, group=None, direction=1, peers=None, ou
     tmp = ops.empty(rg * cols)
     # [rg][world][wc] -> [world][rg][wc]: destination-major send buffer
     ops.swap_leading(block, tmp, rg, world, wc)
-    _all_to_all(block, tmp, group)                 # received [source][rg][wc] = [rows][wc]: my column slab
+    _all_to_all(block, tmp, group, ops)            # received [source][rg][wc] = [rows][wc]: my column slab
     ops.fft_strided(block, block, 1, rows, wc, direction)      # every column (fft/fft.go:138-144)
-    _all_to_all(tmp, block, group)                 # rows [h*rg, (h+1)*rg) back to rank h: [source][rg][wc]
+    _all_to_all(tmp, block, group, ops)            # rows [h*rg, (h+1)*rg) back to rank h: [source][rg][wc]
     ops.swap_leading(tmp, block, world, rg, wc)    # -> [rg][cols]
     ops.fft_rows(block, tmp, cols, rg, direction)  # every row (fft/fft.go:146-151)
     return tmp
