@@ -221,6 +221,32 @@ def test_tma_fused_stress(gd, delay):             # race hunt: every row of ever
         capi.check(L.gd_set_option(b"tma_delay", SCHEDULE_DEFAULTS["tma_delay"]))
 
 
+def test_tma14_fused_stress(gd):                  # the same race hunt for the fused 2^14 kernel, both modes (Parseval per line)
+    _, capi, L = gd
+    import torch
+    n, nb, reps = 1 << 14, 2048, 40
+    x = torch.empty(nb * n * 2, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), nb * n * 2, 3, 0, None))
+    capi.check(L.gd_stream_sync(None))
+    xc = torch.view_as_complex(x.view(-1, 2))
+    ex_rows = (xc.view(nb, n).abs() ** 2).sum(1)            # rows: nb transforms of 2^14 points
+    ex_cols = (xc.view(n, nb).abs() ** 2).sum(0)            # columns of a 2^14 x nb matrix
+    for _ in range(reps):
+        y.zero_()
+        torch.cuda.synchronize()
+        capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, nb, 1, None))
+        capi.check(L.gd_stream_sync(None))
+        ey = (torch.view_as_complex(y.view(-1, 2)).view(nb, n).abs() ** 2).sum(1)
+        assert float(((ey / n - ex_rows).abs() / ex_rows).max()) < 1e-13
+        y.zero_()
+        torch.cuda.synchronize()
+        capi.check(L.gd_fft_strided_c2c_dev(x.data_ptr(), y.data_ptr(), 1, n, nb, 1, None))
+        capi.check(L.gd_stream_sync(None))
+        ey = (torch.view_as_complex(y.view(-1, 2)).view(n, nb).abs() ** 2).sum(0)
+        assert float(((ey / n - ex_cols).abs() / ex_cols).max()) < 1e-13
+
+
 def test_tma_fused_chunking(gd):                  # more than one 128-transform launch, a partial last chunk, in place
     _, capi, L = gd
     import torch
