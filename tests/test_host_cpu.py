@@ -140,3 +140,21 @@ def test_sharding_partitions():
         segs = [sharding.pwelch_segment_range(r, world, 1 << 20, 4096, 2048) for r in range(world)]
         assert segs[0][0] == 0 and segs[-1][1] == sharding.segment_count(1 << 20, 4096, 2048)
         assert all(a[1] == b[0] for a, b in zip(segs, segs[1:])) and segs[-1][3] <= 1 << 20
+
+
+def test_generated_codelets_are_current_and_correct():
+    """tools/gen_codelets.py: the committed fft_codelets.cuh is what the generator emits, every codelet's DAG evaluates to
+    the DFT (checked in Python against exactly reduced roots), and the operation counts DESIGN.md quotes hold."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_codelets", os.path.join(ROOT, "tools", "gen_codelets.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    want = {4: 16, 8: 52, 16: 144, 32: 376}
+    plans = {4: [4], 8: [2, 4], 16: [4, 4], 32: [4, 2, 4]}
+    for n, ops in want.items():
+        assert g.check(n, plans[n]) < 1e-13 * n
+        _, total, nops = g.codelet(n, plans[n], "x", n < 32)
+        assert total == ops and nops["mul"] == 0
+    text = open(os.path.join(ROOT, "go-dsp_b200", "csrc", "fft_codelets.cuh")).read()
+    for n, ops in want.items():
+        assert "forward %d-point DFT, natural order in and out: %d FP64 instructions" % (n, ops) in text
