@@ -14,6 +14,7 @@
 //       P2: rows n2 of Int[tb][.][k1][.]   -> M'[k1 + 128 k2][t]
 // A phase (the unit of the dependency counters) is 256 tiles = 2^20 points = one 16 MiB slot: 64 transforms (ROWS) or
 // 64 columns (COLS).
+// PROF: cycle counters of the consumer groups (tools/exp_fft2_axes.py --prof only).
 // Consumer group = 4 warps: lane = line, warp j = residue of the point index mod 4. 128 = 32 x 4: a radix-32 step on
 // points j + 4 i, the twiddle w_128^(j k) (warp-uniform, read from the kernel parameters: no product chains), one
 // shared-memory exchange, eight radix-4 butterflies.
@@ -41,6 +42,10 @@ struct Tma14Params {
     const cpx* tw_hi;
     double scale;                // inverse: 1/N folded into the four-step twiddle
     cpx w128[3][32];             // w_128^(j k), j = 1..3, k < 32
+    cpx* out;                    // opt bit 0 only: pass-2 output from registers (512-byte rows: one warp store each)
+    int opt;                     // experiments: bit 0 = pass-2 output straight from registers (no staging, no TMA tile store)
+    long long out_dist;          //   ROWS: transform t at out + t * out_dist;  COLS: row pitch of the matrix (columns)
+    long long* prof;             // measurement: [gridDim.x][16] cycle counters of the consumer groups (null in the product)
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned long long* bar) {
@@ -66,7 +71,7 @@ __device__ __forceinline__ void t14_coords(int type, int grp, int c, int h, int 
     }
 }
 
-template <int MODE, bool INV>
+template <int MODE, bool INV, bool PROF>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_int,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ Tma14Params a) {
@@ -153,14 +158,19 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const unsigned long long pol_last = policy_evict_last();
             unsigned ns = 0;
             int free_tf = S - 1;
+            long long c_staged = 0, c_slot = 0, c_read = 0, c_pub = 0;
             for (int it = g;; it += 2) {
                 while (ld_volatile_shared(log_count) <= it) __nanosleep(64);
                 __threadfence_block();
                 const int item = log[it & 31];
                 if (item < 0) break;
                 const TmaItem pi = tma_decode(item, B, D);
+                if (pi.type == 1 && (a.opt & 1)) continue;  // experiment: pass-2 tiles stored by the consumers themselves (nothing staged)
+                long long t0 = 0;
+                if (PROF) t0 = clock64();
                 mbar_wait(staged + g, ns & 1);
                 ns++;
+                if (PROF) { const long long t1 = clock64(); c_staged += t1 - t0; t0 = t1; }
                 const cpx* srcb = work + (size_t)g * T14_WELEMS;
                 if (pi.type == 1) {
                     int c0, c1, c2, c3;
@@ -171,9 +181,12 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     tma_store_4d(&tm_out, c0, c1, c2, c3, srcb + HALF_ELEMS);
                     tma_commit();
                 } else {
+                    // the slot is free once pass 2 of the phase that used it is complete (polling earlier, while the tile is
+                    // still being computed, was slower: cols 2.14 -> 2.48 ms)
                     if (pi.tf > free_tf) {
                         while (ld_relaxed_gpu(a.done2 + (pi.tf - S)) < TPT) __nanosleep(32);
                         free_tf = pi.tf;
+                        if (PROF) { const long long t1 = clock64(); c_slot += t1 - t0; t0 = t1; }
                     }
                     cpx* slot = a.scratch + (size_t)(pi.tf % S) * ((size_t)1 << 20);
                     if constexpr (MODE == T14_ROWS) {
@@ -198,13 +211,16 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 mbar_arrive(drained + 2 * g);
                 tma_wait_read0();
                 mbar_arrive(drained + 2 * g + 1);
+                if (PROF) { const long long t1 = clock64(); c_read += t1 - t0; t0 = t1; }
                 if (pi.type == 0) {
                     tma_wait_all0();
                     asm volatile("fence.proxy.async.global;\n" ::: "memory");
                     red_release_gpu(a.done1 + pi.tf, 1);
+                    if (PROF) c_pub += clock64() - t0;
                 }
             }
             tma_wait_all0();
+            if (PROF) { long long* q = a.prof + (size_t)blockIdx.x * TMA_PROF_SLOTS + 16 + 4 * g; q[0] = c_staged; q[1] = c_slot; q[2] = c_read; q[3] = c_pub; }
         }
         return;
     }
@@ -214,16 +230,20 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int j = warp & 3, ell = tid & 31;                 // point residue mod 4 (warp-uniform), line
     cpx* wbuf = work + (size_t)g * T14_WELEMS;
     unsigned nrd = 0, nst = 0;
-    bool first = true;
+    bool prev_staged = false;                               // the previous tile left staged output in the work buffer (pass 1 only)
     unsigned fph = 0;
+    long long c_full0_p1 = 0, c_full0_p2 = 0, c_full1 = 0, c_drain = 0, c_rd = 0, c_bar = 0, n_tiles = 0, t_start = 0, t0 = 0;
+    if (PROF) t_start = clock64();
     for (int it = g;; it += 2) {
         const long long h0 = 2LL * it;
         const int s0 = (int)(h0 % TMA_NSLOT), s1 = (int)((h0 + 1) % TMA_NSLOT);
+        if (PROF) t0 = clock64();
         mbar_wait(full_h + 2 * s0 + g, (fph >> s0) & 1);
         fph ^= 1u << s0;
         const int item = log[it & 31];
         if (item < 0) break;
         const TmaItem wi = tma_decode(item, B, D);
+        if (PROF) { const long long dt = clock64() - t0; if (wi.type == 0) c_full0_p1 += dt; else c_full0_p2 += dt; n_tiles++; }
         const unsigned ld_conj = (INV && wi.type == 0) ? 0x80000000u : 0u;
         cpx x[32];
         {   // points j + 4 i of line ell: rows j + 4 i of the tile, i < 16 in the first half
@@ -232,8 +252,10 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             for (int i = 0; i < 16; i++) x[i] = INV ? cconj_if(s[i * 4 * T14_LINES], ld_conj) : s[i * 4 * T14_LINES];
         }
         mbar_arrive(freed_h + s0);
+        if (PROF) t0 = clock64();
         mbar_wait(full_h + 2 * s1 + g, (fph >> s1) & 1);
         fph ^= 1u << s1;
+        if (PROF) c_full1 += clock64() - t0;
         if (wi.type == 1 && tid == g * TMA_GROUP) red_relaxed_gpu(a.done2 + wi.tf, 1);
         {
             const cpx* s = land + (size_t)s1 * HALF_ELEMS + j * T14_LINES + ell;
@@ -246,18 +268,21 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
             for (int k = 1; k < 32; k++) x[k] = cmul(x[k], a.w128[j - 1][k]);
         }
-        if (!first) mbar_wait(drained + 2 * g, (nst - 1) & 1);
+        if (PROF) t0 = clock64();
+        if (prev_staged) mbar_wait(drained + 2 * g, (nst - 1) & 1);
+        if (PROF) c_drain += clock64() - t0;
         // exchange: Y_j[k] -> row 4 k + j of the work buffer, column ell; thread (ell, j') then takes rows 32 j' .. 32 j' + 31,
         // i.e. k = 8 j' + k_lo, all four j
         {
             cpx* s = wbuf + j * T14_LINES + ell;
 #pragma unroll
             for (int k = 0; k < 16; k++) s[k * 4 * T14_LINES] = x[k];                        // rows < 64
-            if (!first) mbar_wait(drained + 2 * g + 1, (nst - 1) & 1);
+            if (PROF) t0 = clock64();
+            if (prev_staged) mbar_wait(drained + 2 * g + 1, (nst - 1) & 1);
+            if (PROF) c_drain += clock64() - t0;
 #pragma unroll
             for (int k = 16; k < 32; k++) s[k * 4 * T14_LINES] = x[k];
         }
-        first = false;
         // four-step twiddle bases of this line (pass 1): w^(n2 * 8 j'), w^(n2), w^(32 n2)
         cpx tb0, tb1, tb32;
         if (wi.type == 0) {
@@ -268,7 +293,9 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             tb32 = cmul(__ldg(a.tw_hi + (e32 >> 12)), __ldg(a.tw_lo + (e32 & 4095u)));
             if (INV) tb0 = make_double2(tb0.x * a.scale, tb0.y * a.scale);
         }
+        if (PROF) t0 = clock64();
         group_bar(1 + g);
+        if (PROF) c_bar += clock64() - t0;
         {
             const cpx* s = wbuf + (32 * j) * T14_LINES + ell;
 #pragma unroll
@@ -277,8 +304,10 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         mbar_arrive(rd + g);
 #pragma unroll
         for (int kl = 0; kl < 8; kl++) dft4<1>(&x[4 * kl]);                                  // x[4 k_lo + m] = X[8 j + k_lo + 32 m]
+        if (PROF) t0 = clock64();
         mbar_wait(rd + g, nrd & 1);                         // every gather of this tile is done: the buffer may be overwritten
         nrd++;
+        if (PROF) c_rd += clock64() - t0;
         if (wi.type == 0) {
             // x[4 k_lo + m] *= w^(n2 (8 j + k_lo + 32 m)) = tb0 * tb1^k_lo * tb32^m
             cpx c[8];
@@ -306,7 +335,11 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
                     for (int m = 0; m < 4; m++) s[(kl + 32 * m) * T14_LINES] = x[4 * kl + m];
             }
-        } else {
+            fence_proxy_async();
+            mbar_arrive(staged + g);
+            nst++;
+            prev_staged = true;
+        } else if (!(a.opt & 1)) {
             cpx* s = wbuf + (8 * j) * T14_LINES + ell;       // X[k2 = 8 j + k_lo + 32 m]: row k2 of the tile, column = line
 #pragma unroll
             for (int kl = 0; kl < 8; kl++)
@@ -315,10 +348,37 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     const cpx v = x[4 * kl + m];
                     s[(kl + 32 * m) * T14_LINES] = INV ? make_double2(v.x, -v.y) : v;
                 }
+            fence_proxy_async();
+            mbar_arrive(staged + g);
+            nst++;
+            prev_staged = true;
+        } else {
+            // experiment (tma_opt=16): X[k2 = 8 j + k_lo + 32 m] of line ell, the 32 lanes of a warp write one 512-byte row per
+            // store. Measured equal to the staged path within run-to-run noise (profiles/r2_exp_fft2_axes_prof.jsonl): the
+            // wait for the work buffer comes from the pass-1 bulk stores, not from the pass-2 tile stores.
+            cpx* dst;
+            long long pitch;
+            if constexpr (MODE == T14_ROWS) {
+                dst = a.out + (long long)(wi.tf * 64 + (wi.c >> 2)) * a.out_dist + (wi.c & 3) * 32 + ell;
+                pitch = T14_LEN;
+            } else {
+                dst = a.out + (long long)(wi.c & 127) * a.out_dist + (long long)(wi.tf * 2 + (wi.c >> 7)) * 32 + ell;
+                pitch = (long long)T14_LEN * a.out_dist;
+            }
+            dst += (long long)(8 * j) * pitch;
+#pragma unroll
+            for (int kl = 0; kl < 8; kl++)
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const cpx v = x[4 * kl + m];
+                    __stcs(reinterpret_cast<double2*>(dst + (long long)(kl + 32 * m) * pitch), INV ? make_double2(v.x, -v.y) : v);
+                }
+            prev_staged = false;
         }
-        fence_proxy_async();
-        mbar_arrive(staged + g);
-        nst++;
+    }
+    if (PROF && (tid & (TMA_GROUP - 1)) == 0) {
+        long long* q = a.prof + (size_t)blockIdx.x * TMA_PROF_SLOTS + 8 * g;
+        q[0] = c_full0_p1; q[1] = c_full0_p2; q[2] = c_full1; q[3] = c_drain; q[4] = c_rd; q[5] = c_bar; q[6] = clock64() - t_start; q[7] = n_tiles;
     }
 }
 

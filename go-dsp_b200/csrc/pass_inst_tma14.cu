@@ -47,11 +47,11 @@ bool tma14_cols_applicable(const cpx* src, const cpx* dst, long long len, long l
     return len == 16384 && s >= 128 && s % 64 == 0 && s < (1LL << 30) && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
 }
 
-template <int MODE, bool INV>
+template <int MODE, bool INV, bool PROF = false>
 static cudaError_t launch14(int grid, const CUtensorMap& mx, const CUtensorMap& mi, const CUtensorMap& mo, const Tma14Params& f, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(fft_tma14_kernel<MODE, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, T14_SMEM);   // per device
+    cudaError_t e = cudaFuncSetAttribute(fft_tma14_kernel<MODE, INV, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, T14_SMEM);   // per device
     if (e != cudaSuccess) return e;
-    fft_tma14_kernel<MODE, INV><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f);
+    fft_tma14_kernel<MODE, INV, PROF><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f);
     return cudaGetLastError();
 }
 
@@ -134,11 +134,22 @@ Status fft_tma_2p14(Device& d, int mode, const cpx* in, long long in_dist, cpx* 
         f.batch = (int)ng; f.delay = D; f.nslots = S; f.scratch = scratch;
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.scale = scale;
+        f.out = mode == T14_ROWS ? out + g0 * 64 * out_dist : out + g0 * 64;
+        f.out_dist = mode == T14_ROWS ? out_dist : count;
+        f.opt = d.tma_opt >> 4;
+        f.prof = nullptr;
+        if (d.tma_prof) {
+            long long* pr;
+            GD_TRY(d.ensure_scratch(SCR_PROF, (size_t)d.num_sms * TMA_PROF_SLOTS * sizeof(long long), (void**)&pr));
+            GD_CUDA(cudaMemsetAsync(pr, 0, (size_t)d.num_sms * TMA_PROF_SLOTS * sizeof(long long), st));
+            f.prof = pr;
+        }
         cudaError_t e = cudaMemsetAsync(cnt, 0, (2 * (size_t)CH + 2) * sizeof(int), st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(counters)"); break; }
         const long long nitems = 2 * ng * 256;
         const int grid = (int)(nitems < d.num_sms ? nitems : d.num_sms);
-        if (mode == T14_ROWS) e = inv ? launch14<T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
+        if (f.prof && !inv) e = mode == T14_ROWS ? launch14<T14_ROWS, false, true>(grid, m_x, m_int, m_out, f, st) : launch14<T14_COLS, false, true>(grid, m_x, m_int, m_out, f, st);
+        else if (mode == T14_ROWS) e = inv ? launch14<T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
         else e = inv ? launch14<T14_COLS, true>(grid, m_x, m_int, m_out, f, st) : launch14<T14_COLS, false>(grid, m_x, m_int, m_out, f, st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "fft_tma14_kernel launch"); break; }
         g_launches++;

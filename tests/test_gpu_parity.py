@@ -302,6 +302,14 @@ def test_fft2_fused_2p14_lines(gd, rows, cols):  # the fused 2^14 kernel (fft_tm
     finally:
         capi.check(L.gd_set_option(b"tma14", 1))
     assert rel_l2(o2, out) <= 1e-14
+    capi.check(L.gd_set_option(b"tma_opt", 16))  # experiment path: pass-2 output stored from registers; same bits
+    try:
+        o3, b3 = np.empty_like(x), np.empty_like(x)
+        capi.check(L.gd_fft2_c2c(x.ctypes.data, o3.ctypes.data, rows, cols, 1))
+        capi.check(L.gd_fft2_c2c(o3.ctypes.data, b3.ctypes.data, rows, cols, -1))
+    finally:
+        capi.check(L.gd_set_option(b"tma_opt", 0))
+    assert np.array_equal(o3, out) and np.array_equal(b3, back)
 
 
 def test_fft2_16384_square_sampled(gd):          # config C3: the full 16384 x 16384 matrix, device resident
