@@ -329,6 +329,7 @@ static int set_option_one(Device& d, const char* key, int64_t value) {
     else if (!strcmp(key, "fourstep_pipeline_mb")) { if (value < 1) return (int)invalid_arg("fourstep_pipeline_mb < 1"); d.fourstep_pipeline_mb = (int)value; }
     else if (!strcmp(key, "wide_tiles")) d.wide_tiles = value != 0;
     else if (!strcmp(key, "fused")) d.use_fused = value != 0;
+    else if (!strcmp(key, "bluestein_fused")) d.bluestein_fused = value != 0;
     else if (!strcmp(key, "debug_alias")) d.debug_alias = value != 0;
     else if (!strcmp(key, "w32")) { if (value < 0 || value > 6) return (int)invalid_arg("w32 out of range"); d.w32 = (int)value; }
     else if (!strcmp(key, "tma")) d.use_tma = value != 0;

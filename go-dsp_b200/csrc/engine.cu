@@ -8,12 +8,14 @@
 
 #include "fft_fused.cuh"
 #include "pass_launch.cuh"
+#include "bluestein_small.cuh"
 
 namespace gd {
 
 cudaError_t launch_fused(int log2l, bool wide, const FusedParams& a, long long total_items, int num_sms, cudaStream_t st);
 int fused_tile_lines(int log2l, bool wide);
 cudaError_t launch_pass32(int variant, const PassParams& a, int num_sms, cudaStream_t st);
+cudaError_t launch_bluestein_small(int log2la, const BluesteinSmallParams& a, int num_sms, cudaStream_t st);
 bool tma_fused_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, int ld_conj, int st_conj, double scale);
 Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long batch, int ld_conj,
                     int st_conj, double scale, cudaStream_t st);
@@ -727,6 +729,19 @@ static Status bluestein_fft(Device& d, const void* in, long long in_dist, cpx* o
     const BluesteinPlan* pl;
     GD_TRY(d.bluestein(n, st, &pl));
     const long long la = pl->la;
+    if (pl->log2la <= 12 && d.bluestein_fused) {
+        // the whole transform of a line in one kernel, the padded sequence stays on the SM (bluestein_small.cuh)
+        BluesteinSmallParams b;
+        b.in = in; b.out = out; b.in_dist = in_dist; b.out_dist = out_dist; b.n = n; b.batch = batch;
+        b.chirp = pl->chirp_inv; b.bhat = pl->bhat; b.wl = pl->log2la >= 5 ? d.wl[pl->log2la] : nullptr;
+        b.scale = 1.0 / (double)la; b.div = (double)n;
+        b.real_in = real_in ? 1 : 0; b.inverse = dir < 0 ? 1 : 0;
+        GD_TRY(d.l2_release());
+        cudaError_t e = launch_bluestein_small(pl->log2la, b, d.num_sms, st);
+        if (e != cudaSuccess) return cuda_fail(e, "bluestein_small_kernel launch");
+        g_launches++;
+        return GD_OK;
+    }
     long long chunk = (long long)((64ull << 20) / ((size_t)la * sizeof(cpx)));
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;

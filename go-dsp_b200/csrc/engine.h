@@ -100,6 +100,7 @@ struct Device {
     size_t l2_carved = 0;                // current cudaLimitPersistingL2CacheSize on this device
     bool l2_dirty = false;               // persisting lines / set-aside left behind by a fused launch
     int fused_delay = 2;                 // phases between P1(g) and P2(g) in the fused schedule
+    bool bluestein_fused = true;         // padded length <= 4096: one kernel per Bluestein transform (bluestein_small.cuh)
     bool use_fused = false;              // one persistent kernel for both four-step passes (N = L*L), L2-resident scratch
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)

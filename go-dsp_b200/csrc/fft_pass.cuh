@@ -164,6 +164,32 @@ __device__ __forceinline__ void gather_step(cpx (&x)[16], int p, const cpx* __re
     }
 }
 
+// One whole line transform on data already in registers: thread p of the line holds x[n = p + P i] on entry and
+// X[k = p + P i] on return (the row-mode layout of fft_pass_kernel on both sides). Every thread of the CTA must call it
+// (CTA-wide barriers); the line's exchange region sl is free again on return.
+template <int LOG2L>
+__device__ __forceinline__ void line_transform(cpx (&x)[16], int p, cpx* __restrict__ sl, const cpx* __restrict__ wl) {
+    using SH = PassShape<LOG2L>;
+    constexpr int L = SH::L;
+    if constexpr (LOG2L <= 4) {
+        dft<L, 1>(x);
+    } else {
+        butterfly_step<L, 16, 1>(x, p, wl);
+        scatter_step<L, 16, 1>(x, p, sl);
+        __syncthreads();
+        gather_step<L>(x, p, sl);
+        if constexpr (SH::NSTEP == 3) {
+            __syncthreads();
+            butterfly_step<L, 16, 16>(x, p, wl);
+            scatter_step<L, 16, 16>(x, p, sl);
+            __syncthreads();
+            gather_step<L>(x, p, sl);
+        }
+        __syncthreads();
+        butterfly_step<L, SH::LASTR, (SH::NSTEP == 2 ? 16 : 256)>(x, p, wl);
+    }
+}
+
 // per-tile addressing of one thread
 struct LineRef {
     long long q, ii;

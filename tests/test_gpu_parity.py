@@ -109,6 +109,35 @@ def test_bluestein_sizes(gd, n):                 # config C2 is n = 1,000,003 (l
     assert rel_l2(godsp.fft.IFFTReal(r), oracle.ifft_real(r)) <= TOL
 
 
+@pytest.mark.parametrize("n", [3, 5, 6, 7, 9, 17, 33, 100, 129, 257, 1000, 1025, 2047])
+def test_bluestein_fused_small(gd, n):           # padded length <= 4096: one kernel per transform (bluestein_small.cuh)
+    """Batched lines (ragged batch: not a multiple of the lines per CTA) against the oracle, forward and inverse, complex
+    and real input; and the two-launch path it replaces gives the same bits (same operations in the same order)."""
+    godsp, capi, L = gd
+    assert L.gd_bluestein_padded_len(n) <= 4096
+    b = 131 if n < 300 else 7
+    x = oracle.splitmix_complex(b * n, 11).reshape(b, n)
+    want = np.stack([oracle.fft(x[i]) for i in range(b)])
+    wanti = np.stack([oracle.ifft(x[i]) for i in range(b)])
+    got, goti = np.empty_like(x), np.empty_like(x)
+    capi.check(L.gd_fft_batch_c2c(x.ctypes.data, got.ctypes.data, n, b, 1))
+    capi.check(L.gd_fft_batch_c2c(x.ctypes.data, goti.ctypes.data, n, b, -1))
+    assert rel_l2(got, want) <= TOL and rel_l2(goti, wanti) <= TOL
+    r = oracle.fill_splitmix(n, 4)
+    gr, gri = godsp.fft.FFTReal(r), godsp.fft.IFFTReal(r)
+    assert rel_l2(gr, oracle.fft_real(r)) <= TOL and rel_l2(gri, oracle.ifft_real(r)) <= TOL
+    capi.check(L.gd_set_option(b"bluestein_fused", 0))
+    try:
+        g2, g2i = np.empty_like(x), np.empty_like(x)
+        capi.check(L.gd_fft_batch_c2c(x.ctypes.data, g2.ctypes.data, n, b, 1))
+        capi.check(L.gd_fft_batch_c2c(x.ctypes.data, g2i.ctypes.data, n, b, -1))
+        r2, r2i = godsp.fft.FFTReal(r), godsp.fft.IFFTReal(r)
+    finally:
+        capi.check(L.gd_set_option(b"bluestein_fused", 1))
+    assert np.array_equal(got, g2) and np.array_equal(goti, g2i)
+    assert np.array_equal(gr, r2) and np.array_equal(gri, r2i)
+
+
 def test_real_roundtrips(gd):                    # C2: IFFT(FFTReal(x)) ~ x and FFT(IFFTReal(x)) ~ x
     godsp = gd[0]
     for n in (4096, 1000003, 1 << 16):
