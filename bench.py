@@ -680,6 +680,24 @@ def run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed):
     def step():
         D.fft_1d_sharded(src, n, ops, work=work, peer=px)       # the peer-memory path leaves its input untouched
     ms, launches, clocks = timed(step, steps, warmup)
+    # per phase, outside the timed region (CUDA events on the ops stream, every phase between two rendezvous, max over ranks)
+    def phase_ms(fn):
+        px.fence()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return allmax(torch, dist, world, e0.elapsed_time(e1))
+    phases = {"lines_n1_ms": phase_ms(lambda: ops.fft_strided(src, work, 1, n1, w, 1)),
+              "twiddle_transpose_nvlink_stores_ms": phase_ms(lambda: px.exchange(work, n1, w, lg)),
+              "lines_n2_ms": phase_ms(lambda: ops.fft_strided(px.recv, work, 1, n2, k, 1))}
+    nv_bytes = 16 * (n // world) * (world - 1) // world
+    phases["nvlink_out_gbs_per_gpu"] = nv_bytes / (phases["twiddle_transpose_nvlink_stores_ms"] * 1e-3) / 1e9 if world > 1 else 0.0
+    phases["lines_hbm_frac"] = 32.0 * (n // world) / (phases["lines_n1_ms"] * 1e-3) / 1e9 / peaks()[0]
+    step()                                                      # `work` holds the whole transform again
+    torch.cuda.synchronize()
     # Parseval on the last step: sum |X|^2 = n * sum |x|^2 over all ranks
     e = torch.stack([(work.real ** 2 + work.imag ** 2).sum(), (src.real ** 2 + src.imag ** 2).sum()])
     dist.all_reduce(e)
@@ -692,8 +710,8 @@ def run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed):
     return {"_parity": par, "metric": "single 1-D FFT GS/s (complex128, 2^%d points over %d GPUs)" % (lg, world), "value": n / (ms * 1e-3) / 1e9,
             "unit": "GS/s", "ms_per_step": ms, "scaling": "weak", "log2n": lg,
             "api": "godsp.distributed.fft_1d_sharded(peer=PeerExchange): strided lines, ONE kernel for twiddle + transpose + NVLink P2P stores into the peers' buffers (gd_fourstep_exchange_dev), strided lines",
-            "nccl_all_to_all_variant_ms": ms_nccl,
-            "all_to_all_bytes_per_gpu": 16 * (n // world) * (world - 1) // world,
+            "nccl_all_to_all_variant_ms": ms_nccl, "phases": phases,
+            "all_to_all_bytes_per_gpu": nv_bytes,
             "parseval_rel_err": parseval,
             "clocks": clocks, "_launches": int(launches), "_peer": px}
 

@@ -105,6 +105,7 @@ Status Device::init(int device, int lane_index) {
     if (const char* s = getenv("GD_TILED")) tiled_scratch = atoi(s) != 0;
     if (const char* s = getenv("GD_W32")) w32 = atoi(s);
     if (const char* s = getenv("GD_TMA")) use_tma = atoi(s) != 0;
+    if (const char* s = getenv("GD_TMA_OPT")) tma_opt = atoi(s);
     if (const char* s = getenv("GD_L2_WINDOW")) use_l2_window = atoi(s) != 0;
     if (const char* s = getenv("GD_FUSED_DELAY")) { int v = atoi(s); if (v >= 1 && v <= 6) fused_delay = v; }
     // the persisting L2 set-aside is one per GPU: only lane 0 carves and resets it (the other lanes' fused kernels run
@@ -453,6 +454,35 @@ __global__ void chirp_kernel(long long n, long long la, cpx* chirp_inv, cpx* b) 
     if (i != 0) b[la - i] = make_double2(c, s);
 }
 
+// Bluestein above a padded length of 2^24 (the power-of-two transforms there are the outer four-step, which takes no fused
+// load / store operators): the same element operations as LD_PAD | LD_MULAUX | LD_REAL | LD_REVERSE and
+// ST_MULAUX | ST_TRUNC | ST_DIV of the pass kernel, as two streaming kernels.
+__global__ void bluestein_prep_kernel(const void* __restrict__ in, int real_in, int reverse, long long n, long long la,
+                                      const cpx* __restrict__ chirp_inv, cpx* __restrict__ a) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < la; i += stride) {
+        cpx v = make_double2(0.0, 0.0);
+        if (i < n) {
+            const long long src = (reverse && i != 0) ? n - i : i;          // fft/fft.go:39-43
+            if (real_in) v.x = __ldg(reinterpret_cast<const double*>(in) + src);
+            else v = __ldg(reinterpret_cast<const cpx*>(in) + src);
+            v = cmul(v, __ldg(chirp_inv + i));                              // fft/bluestein.go:70-73
+        }
+        a[i] = v;
+    }
+}
+__global__ void bluestein_post_kernel(const cpx* __restrict__ r, const cpx* __restrict__ chirp_inv, long long n, int inverse,
+                                      double div, cpx* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        cpx v = cmul(r[i], __ldg(chirp_inv + i));                           // fft/bluestein.go:89-91
+        if (inverse) { v.x /= div; v.y /= div; }                            // fft/fft.go:47-50
+        out[i] = v;
+    }
+}
+
 __global__ void pointwise_mul_kernel(cpx* a, const cpx* b, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) a[i] = cmul(a[i], b[i]);
@@ -707,7 +737,7 @@ Status Device::bluestein(long long n, cudaStream_t st, const BluesteinPlan** out
         long long need = 2 * n - 1;                 // dsputils.NextPowerOf2(2N-1), dsputils/dsputils.go:39-45
         pl.la = 1; pl.log2la = 0;
         while (pl.la < need) { pl.la <<= 1; pl.log2la++; }
-        if (pl.log2la > 24) return invalid("bluestein: padded length > 2^24 not supported");
+        if (pl.log2la > 30) return invalid("bluestein: padded length > 2^30 not supported");
         GD_CUDA(cudaMalloc((void**)&pl.chirp_inv, (size_t)n * sizeof(cpx)));
         GD_CUDA(cudaMalloc((void**)&pl.bhat, (size_t)pl.la * sizeof(cpx)));
         cpx* b;
@@ -740,6 +770,28 @@ static Status bluestein_fft(Device& d, const void* in, long long in_dist, cpx* o
         cudaError_t e = launch_bluestein_small(pl->log2la, b, d.num_sms, st);
         if (e != cudaSuccess) return cuda_fail(e, "bluestein_small_kernel launch");
         g_launches++;
+        return GD_OK;
+    }
+    if (pl->log2la > 24) {
+        // padded length 2^25 .. 2^30: the power-of-two transforms are the outer four-step (plain forward / inverse only), so
+        // the chirp products, the padding and the truncation run as streaming kernels around them; one line at a time
+        cpx* A;
+        GD_TRY(d.ensure_scratch(SCR_A, (size_t)la * sizeof(cpx), (void**)&A));
+        const unsigned g = (unsigned)(d.num_sms * 8);
+        FusedOps fwd, inv;
+        inv.ld_flags = LD_CONJ; inv.st_flags = ST_CONJ | ST_SCALE; inv.scale = 1.0 / (double)la;
+        for (long long b = 0; b < batch; b++) {
+            const void* src = real_in ? (const void*)((const double*)in + b * in_dist) : (const void*)((const cpx*)in + b * in_dist);
+            bluestein_prep_kernel<<<g, 256, 0, st>>>(src, real_in ? 1 : 0, dir < 0 ? 1 : 0, n, la, pl->chirp_inv, A);
+            GD_CUDA(cudaGetLastError());
+            GD_TRY(fft_pow2(d, A, la, A, la, pl->log2la, 1, fwd, st));
+            pointwise_mul_kernel<<<grid_for(la, 256), 256, 0, st>>>(A, pl->bhat, la);
+            GD_CUDA(cudaGetLastError());
+            GD_TRY(fft_pow2(d, A, la, A, la, pl->log2la, 1, inv, st));
+            bluestein_post_kernel<<<g, 256, 0, st>>>(A, pl->chirp_inv, n, dir < 0 ? 1 : 0, (double)n, out + b * out_dist);
+            GD_CUDA(cudaGetLastError());
+            g_launches += 3;
+        }
         return GD_OK;
     }
     long long chunk = (long long)((64ull << 20) / ((size_t)la * sizeof(cpx)));

@@ -109,6 +109,21 @@ def test_bluestein_sizes(gd, n):                 # config C2 is n = 1,000,003 (l
     assert rel_l2(godsp.fft.IFFTReal(r), oracle.ifft_real(r)) <= TOL
 
 
+def test_bluestein_above_2p24(gd):
+    """Non-power-of-two lengths whose padded length exceeds 2^24 (n > 2^23; the reference has no length limit,
+    fft/fft.go:72-87): chirp products and padding as streaming kernels around the outer four-step transforms."""
+    godsp, capi, L = gd
+    n = 8500003
+    assert L.gd_bluestein_padded_len(n) == 1 << 25
+    x = oracle.splitmix_complex(n, 2)
+    got = godsp.fft.FFT(x)
+    assert rel_l2(got, oracle.fft(x)) <= TOL
+    assert rel_l2(godsp.fft.IFFT(x), oracle.ifft(x)) <= TOL
+    # real input is the same transform of (r, 0): identical bits, no second oracle run needed
+    r = np.ascontiguousarray(x.real)
+    assert np.array_equal(godsp.fft.FFTReal(r), godsp.fft.FFT(r.astype(np.complex128)))
+
+
 @pytest.mark.parametrize("n", [3, 5, 6, 7, 9, 17, 33, 100, 129, 257, 1000, 1025, 2047])
 def test_bluestein_fused_small(gd, n):           # padded length <= 4096: one kernel per transform (bluestein_small.cuh)
     """Batched lines (ragged batch: not a multiple of the lines per CTA) against the oracle, forward and inverse, complex
