@@ -133,6 +133,7 @@ __global__ void add_inplace_kernel(double* tot, const double* part, long long n)
 // After gd_init(ndev > 1) the batched host-pointer entry points split their work over devices 0 .. ndev-1, one host thread
 // per device, each running the single-device path on its share. Threads of one process: no torch, no NCCL.
 std::atomic<int> g_fanout{1};
+std::atomic<int> g_fanout_min_log2n{26};     // single power-of-two transforms of at least this size are sharded over the devices
 thread_local bool t_in_fanout = false;
 
 // CPUs next to a GPU (sysfs local_cpulist of its PCI function); false when the container hides the topology
@@ -324,6 +325,7 @@ static int set_option_one(Device& d, const char* key, int64_t value) {
     else if (!strcmp(key, "chunk_streams")) { if (value < 1 || value > 4) return (int)invalid_arg("chunk_streams out of range"); d.chunk_streams = (int)value; }
     else if (!strcmp(key, "l2_block_window")) d.l2_block_window = value != 0 && d.lane == 0;
     else if (!strcmp(key, "pwelch_bulk")) d.pwelch_bulk = value != 0;
+    else if (!strcmp(key, "fanout_min_log2n")) { if (value < 12 || value > 40) return (int)invalid_arg("fanout_min_log2n out of range"); g_fanout_min_log2n.store((int)value); }
     else if (!strcmp(key, "fourstep_pipeline")) d.fourstep_pipeline = value != 0;
     else if (!strcmp(key, "fourstep_exchange_ctas")) d.fourstep_exchange_ctas = (int)value;
     else if (!strcmp(key, "fourstep_pipeline_mb")) { if (value < 1) return (int)invalid_arg("fourstep_pipeline_mb < 1"); d.fourstep_pipeline_mb = (int)value; }
@@ -367,9 +369,63 @@ int64_t gd_bluestein_padded_len(int64_t n) {
 
 // ---------------------------------------------------------------- host-pointer API
 
+// ONE power-of-two transform of n = N1 * N2 points over `width` devices of this process (BASELINE config C5 without
+// torchrun / NCCL): device g owns the columns [g W, (g + 1) W) of x viewed as [N1][N2]; lines over n1; ONE kernel that multiplies
+// by w_N^(k1 n2), transposes and stores into the peers' receive buffers over NVLink (fourstep_exchange_kernel); lines over n2;
+// device h then holds X[k1 + N1 k2] for k1 in [h K, (h + 1) K). Host <-> device traffic is two strided 2-D copies per device.
+static int fft1d_fanout(const double* in, double* out, int lg, int dir, int width) {
+    const int l1 = (lg + 1) / 2;
+    const long long N1 = 1LL << l1, N2 = 1LL << (lg - l1), K = N1 / width, W = N2 / width, per = K * N2;
+    std::vector<cpx*> A((size_t)width, nullptr), R((size_t)width, nullptr);
+    HostBarrier bar(width);
+    std::atomic<int> failed{0};
+    return fan_out(width, [&](int i) -> int {
+        int rc = 0;
+        auto step = [&](Status s) { if (s != ::gd::GD_OK && !rc) { rc = (int)s; failed.store(1); } };
+        auto cuda_step = [&](cudaError_t e, const char* what) { if (e != cudaSuccess) step(cuda_fail(e, what)); };
+        DevLock L;
+        if (L.st != ::gd::GD_OK) { failed.store(1); rc = (int)L.st; for (int k = 0; k < 2; k++) bar.wait(); return rc; }
+        Device& d = *L.d;
+        ScratchOrder order__(d, d.stream);
+        for (int h = 0; h < width; h++)
+            if (h != i) { cudaError_t e = cudaDeviceEnablePeerAccess(h, 0); if (e != cudaSuccess) cudaGetLastError(); }
+        step(d.ensure_scratch(SCR_STAGE_IN, (size_t)per * sizeof(cpx), (void**)&A[(size_t)i]));
+        step(d.ensure_scratch(SCR_STAGE_OUT, (size_t)per * sizeof(cpx), (void**)&R[(size_t)i]));
+        cpx* a = A[(size_t)i];
+        if (!rc) cuda_step(cudaMemcpy2DAsync(a, (size_t)W * sizeof(cpx), (const cpx*)in + (size_t)i * W, (size_t)N2 * sizeof(cpx),
+                                             (size_t)W * sizeof(cpx), (size_t)N1, cudaMemcpyHostToDevice, d.stream), "cudaMemcpy2DAsync(H2D slab)");
+        if (!rc) step(fft_strided(d, a, a, 1, N1, W, dir, d.stream));                       // lines over n1
+        cudaStreamSynchronize(d.stream);
+        bar.wait();                                                                         // every receive buffer exists and is idle
+        if (!failed.load()) step(fourstep_exchange(a, R.data(), N1, W, i, width, lg, d.stream, 0, -1, 0, dir));
+        cudaStreamSynchronize(d.stream);
+        bar.wait();                                                                         // every device's stores have landed
+        if (!failed.load()) step(fft_strided(d, R[(size_t)i], a, 1, N2, K, dir, d.stream));  // lines over n2: a[k2][k] = X[i K + k + N1 k2]
+        if (!failed.load()) cuda_step(cudaMemcpy2DAsync((cpx*)out + (size_t)i * K, (size_t)N1 * sizeof(cpx), a, (size_t)K * sizeof(cpx),
+                                                        (size_t)K * sizeof(cpx), (size_t)N2, cudaMemcpyDeviceToHost, d.stream), "cudaMemcpy2DAsync(D2H slab)");
+        cudaError_t e = cudaStreamSynchronize(d.stream);
+        if (e != cudaSuccess) step(cuda_fail(e, "fft1d_fanout"));
+        if (!rc && failed.load()) { set_error("another device of the fan-out failed"); rc = (int)::gd::GD_ERR_CUDA; }
+        return rc;
+    });
+}
+static bool all_peers(int width) {
+    for (int a = 0; a < width; a++)
+        for (int b = 0; b < width; b++)
+            if (a != b) { int ok = 0; if (cudaDeviceCanAccessPeer(&ok, a, b) != cudaSuccess || !ok) return false; }
+    return true;
+}
+
 static int fft_host(const double* in, double* out, int64_t n, int64_t batch, bool real_in, int dir) {
     if (!in || !out || n < 1 || batch < 1 || (dir != 1 && dir != -1)) return (int)invalid_arg("fft: bad arguments");
     const int width = fanout_width();
+    if (width > 1 && batch == 1 && !real_in && (n & (n - 1)) == 0 && (width & (width - 1)) == 0 && width <= 16) {
+        // one large power-of-two transform: sharded four-step over the devices of this process
+        int lg = 0;
+        while ((1LL << lg) < n) lg++;
+        const long long n2 = 1LL << (lg - (lg + 1) / 2);
+        if (lg >= g_fanout_min_log2n.load() && lg <= 36 && n2 / width >= 32 && all_peers(width)) return fft1d_fanout(in, out, lg, dir, width);
+    }
     if (width > 1 && batch >= 2 * (int64_t)width && (size_t)batch * (size_t)n >= ((size_t)1 << 22)) {
         // independent transforms: contiguous row ranges, one per device (no collective)
         const size_t in_el = real_in ? 1 : 2;

@@ -170,7 +170,7 @@ Status pwelch_finalize(const double* raw, long long lp, long long nsegs, double 
 Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st, int dir = 1);
 Status repack_gkw(const cpx* in, cpx* out, long long G, long long K, long long W, cudaStream_t st);
 Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,
-                         cudaStream_t st, long long cbeg = 0, long long ccount = -1, int max_ctas = 0);
+                         cudaStream_t st, long long cbeg = 0, long long ccount = -1, int max_ctas = 0, int dir = +1);
 Status fourstep_lines_exchange(Device& d, const cpx* slab, cpx* tmp, cpx* const* peer_recv, long long n1, long long w, int rank, int world,
                                int log2n, cudaStream_t st);
 Status peer_block_copy(const cpx* src, cpx* const* peers, int world, int rank, long long rows, long long cols, long long src_step,

@@ -53,13 +53,15 @@ GD_API int gd_shutdown(void);
 GD_API const char* gd_last_error(void);
 GD_API int gd_device_count(void);            /* devices initialised so far */
 GD_API int gd_use_device(int dev);           /* device used by subsequent calls from this thread (default 0) */
-/* Tuning knobs: "pass_scratch_mb" (inter-pass scratch kept L2-resident), "wide_tiles" (0/1). */
+/* Tuning knobs: "pass_scratch_mb" (inter-pass scratch kept L2-resident), "wide_tiles" (0/1), "fanout_min_log2n". */
 GD_API int gd_set_option(const char* key, int64_t value);
 
 /* ---- fft package ----------------------------------------------------------------------- */
 /* fft.FFT (fft/fft.go:72-87) / fft.IFFT (fft/fft.go:35-52): any n >= 1; power-of-two n runs the
  * Stockham passes that replace radix2FFT (fft/radix2.go:80-154), other n the fused Bluestein path
- * that replaces bluesteinFFT (fft/bluestein.go:68-94). */
+ * that replaces bluesteinFFT (fft/bluestein.go:68-94). After gd_init(ndev > 1), a power-of-two n of at least
+ * 2^26 points (option "fanout_min_log2n") is ONE transform sharded over the devices of the process: four-step
+ * with the twiddle, the transpose and the peer-memory stores over NVLink in one kernel (BASELINE config C5). */
 GD_API int gd_fft_c2c(const double* in, double* out, int64_t n, int dir);
 /* fft.FFTReal / fft.IFFTReal (fft/fft.go:25-32): float64 in, full n-bin complex out; the
  * dsputils.ToComplex widening (dsputils/dsputils.go:25-31) is fused into the first load. */

@@ -55,6 +55,27 @@ capi.check(L.gd_fft2_c2c(m.ctypes.data, o2.ctypes.data, R, Cc, 1))
 assert rel(o2, oracle.fft2(m)) <= 1e-12
 capi.check(L.gd_fft2_c2c(o2.ctypes.data, b2.ctypes.data, R, Cc, -1))
 assert rel(b2, m) <= 1e-12
+# ONE large power-of-two transform: sharded four-step over the devices (lines, fused twiddle + transpose + peer stores, lines),
+# forward against the oracle and inverse as a round trip; first below the default threshold (2^26 points), then at it
+capi.check(L.gd_set_option(b"fanout_min_log2n", 20))
+for lg in (20, 23):
+    n = 1 << lg
+    x = oracle.splitmix_complex(n, 8)
+    out, back = np.empty_like(x), np.empty_like(x)
+    l0 = L.gd_kernel_launches()
+    capi.check(L.gd_fft_c2c(x.ctypes.data, out.ctypes.data, n, 1))
+    nl = L.gd_kernel_launches() - l0
+    assert nl >= 3 * ndev, ("the transform was not sharded", nl)
+    assert rel(out, oracle.fft(x)) <= 1e-12, ("sharded 1-D forward", lg)
+    capi.check(L.gd_fft_c2c(out.ctypes.data, back.ctypes.data, n, -1))
+    assert rel(back, x) <= 1e-12, ("sharded 1-D inverse", lg)
+    assert rel(back, oracle.ifft(out)) <= 1e-12
+capi.check(L.gd_set_option(b"fanout_min_log2n", 26))
+n = 1 << 26
+x = oracle.splitmix_complex(n, 9)
+out = np.empty_like(x)
+capi.check(L.gd_fft_c2c(x.ctypes.data, out.ctypes.data, n, 1))
+assert rel(out, oracle.fft(x)) <= 1e-12, "sharded 1-D forward 2^26"
 print("MULTI_DEVICE_OK", ndev)
 '''
 
