@@ -337,6 +337,7 @@ static int set_option_one(Device& d, const char* key, int64_t value) {
     else if (!strcmp(key, "tma")) d.use_tma = value != 0;
     else if (!strcmp(key, "tma_opt")) d.tma_opt = (int)value;
     else if (!strcmp(key, "tma14")) d.use_tma14 = value != 0;
+    else if (!strcmp(key, "tma16")) d.use_tma16 = value != 0;
     else if (!strcmp(key, "tma_prof")) d.tma_prof = value != 0;
     else if (!strcmp(key, "tma_delay")) { if (value < 0 || value > 4) return (int)invalid_arg("tma_delay out of range"); d.tma_delay = (int)value; }
     else if (!strcmp(key, "tma_slots")) { if (value < 2 || value > 6) return (int)invalid_arg("tma_slots out of range"); d.tma_slots = (int)value; }

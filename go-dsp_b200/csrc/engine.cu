@@ -25,6 +25,11 @@ bool tma14_rows_applicable(const void* in, long long in_dist, const cpx* out, lo
 bool tma14_cols_applicable(const cpx* src, const cpx* dst, long long len, long long s);
 Status fft_tma_2p14(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
                     cudaStream_t st);
+bool tma16_rows_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, long long batch, int ld_conj, int st_conj,
+                           double scale);
+bool tma16_cols_applicable(const cpx* src, const cpx* dst, long long len, long long s);
+Status fft_tma_2p16(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
+                    cudaStream_t st);
 
 // ------------------------------------------------------------------ errors
 std::atomic<long long> g_launches{0};
@@ -314,6 +319,12 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
         if (tma14_rows_applicable(in, in_dist, out, out_dist, batch, lc, sc, scl))
             return fft_tma_2p14(d, 0, (const cpx*)in, in_dist, out, out_dist, batch, lc != 0, scl, st);
+    }
+    if (d.use_tma && d.use_tma16 && lean && log2n == 16 && !d.debug_alias) {
+        const int lc = (ops.ld_flags & LD_CONJ) ? 1 : 0, sc = (ops.st_flags & ST_CONJ) ? 1 : 0;
+        const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
+        if (tma16_rows_applicable(in, in_dist, out, out_dist, batch, lc, sc, scl))
+            return fft_tma_2p16(d, 0, (const cpx*)in, in_dist, out, out_dist, batch, lc != 0, scl, st);
     }
     if (d.use_fused && lean && (log2n % 2) == 0 && log2n >= 16 && batch * (2LL << (log2n / 2)) < (1LL << 30)) {
         // both passes in one persistent kernel, intermediate resident in L2 (fft_fused.cuh)
@@ -954,6 +965,12 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         // every column of a 2^14-row matrix: one fused launch, intermediate resident in L2 (fft_tma14.cuh)
         for (long long o = 0; o < outer; o++)
             GD_TRY(fft_tma_2p14(d, 1, src + o * len * s, 0, dst + o * len * s, 0, s, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
+        return GD_OK;
+    }
+    if (!sub && d.use_tma && d.use_tma16 && tma16_cols_applicable(src, dst, len, s)) {
+        // every column of a 2^16-row matrix (the line passes of the sharded 2^32-point transform): same kernel, 256 x 256
+        for (long long o = 0; o < outer; o++)
+            GD_TRY(fft_tma_2p16(d, 1, src + o * len * s, 0, dst + o * len * s, 0, s, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
         return GD_OK;
     }
     if (p2 && len <= (1LL << 24) && fits31) {

@@ -105,6 +105,7 @@ struct Device {
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)
     bool use_tma14 = true;               // 2^14-point lines (batched rows, columns of a 2^14-row matrix): fused kernel of fft_tma14.cuh
+    bool use_tma16 = true;               // 2^16-point lines: the same kernel with 256-point sub-lines
     int tma_opt = 0;                     // measurement switches of the fused kernel (TmaFusedParams::opt)
     int tma_prof = 0;                    // measurement: cycle counters of the fused kernel (gd_tma_profile_read)
     int tma_delay = 2;                   // P1 phases the schedule runs ahead of P2 (fft_tma.cuh)

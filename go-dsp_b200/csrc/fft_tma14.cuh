@@ -23,10 +23,25 @@
 
 namespace gd {
 
-constexpr int T14_LINES = 32, T14_LEN = 128;
-constexpr int T14_HALF_BYTES = 64 * T14_LINES * 16;                   // 32768
-constexpr int T14_ROWPITCH = T14_LEN + 1;                             // ROWS pass-1 staging: 32 rows of 129 elements (skew: conflict-free)
-constexpr int T14_WBYTES = T14_LINES * T14_ROWPITCH * 16;             // 66048 >= 65536
+// The same kernel serves N = 2^16 = 256 x 256 (LEN = 256): a tile is then 16 adjacent lines of 256 points (256 rows x 256
+// bytes), lane = (line, low bit of the residue mod 8), 256 = 32 x 8: radix-32 step, twiddle w_256^(j k) by a product chain
+// (j differs inside a warp), one exchange, four radix-8 butterflies. Everything else (phases of 256 tiles = 2^20 points,
+// halves of 32 KiB, slots of 16 MiB) is unchanged.
+template <int LEN>
+struct T14Shape {
+    static_assert(LEN == 128 || LEN == 256, "sub-line length");
+    static constexpr int LINES = 4096 / LEN;                          // lines per tile: 32 / 16
+    static constexpr int NJ = LEN / 32;                               // residues of the point index handled by different threads: 4 / 8
+    static constexpr int KB = 32 / NJ;                                // outputs k = KB j' + k_lo + 32 m per thread: 8 / 4
+    static constexpr int TPT = LEN / LINES;                           // ROWS: tiles per transform: 4 / 16
+    static constexpr int TPP = 256 / TPT;                             // ROWS: transforms per phase: 64 / 16
+    static constexpr int TBP = 256 / LEN;                             // COLS: blocks of LINES columns per phase: 2 / 1
+    static constexpr int CPP = TBP * LINES;                           // COLS: columns per phase: 64 / 16
+    static constexpr int ROWPITCH = LEN + 1;                          // ROWS pass-1 staging: LINES rows of LEN + 1 elements (skew: conflict-free)
+    static constexpr int LOG2N = LEN == 128 ? 14 : 16;
+};
+constexpr int T14_HALF_BYTES = 32768;                                 // half a tile: LEN / 2 rows of LINES elements
+constexpr int T14_WBYTES = 32 * 129 * 16;                             // 66048 >= 65536 (LEN = 256: 16 * 257 * 16 = 65792)
 constexpr int T14_WELEMS = T14_WBYTES / 16;
 constexpr int T14_SMEM = TMA_NSLOT * T14_HALF_BYTES + 2 * T14_WBYTES + 1024;     // 231424
 enum : int { T14_ROWS = 0, T14_COLS = 1 };
@@ -38,10 +53,11 @@ struct Tma14Params {
     int* done1;
     int* done2;
     int* queue;
-    const cpx* tw_lo;            // w_16384^e = hi[e >> 12] * lo[e & 4095]
+    const cpx* tw_lo;            // w_N^e = hi[e >> 12] * lo[e & 4095], N = LEN^2
     const cpx* tw_hi;
     double scale;                // inverse: 1/N folded into the four-step twiddle
-    cpx w128[3][32];             // w_128^(j k), j = 1..3, k < 32
+    cpx w128[3][32];             // LEN = 128: w_128^(j k), j = 1..3, k < 32
+    const cpx* wl;               // LEN = 256: exp(-2 pi i p / 256), p < 256
     cpx* out;                    // opt bit 0 only: pass-2 output from registers (512-byte rows: one warp store each)
     int opt;                     // experiments: bit 0 = pass-2 output straight from registers (no staging, no TMA tile store)
     long long out_dist;          //   ROWS: transform t at out + t * out_dist;  COLS: row pitch of the matrix (columns)
@@ -58,20 +74,21 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c0, int 
 }
 
 // tile c of phase (type, grp), half h -> tensor coordinates (in doubles along dim 0)
-template <int MODE>
+template <int LEN, int MODE>
 __device__ __forceinline__ void t14_coords(int type, int grp, int c, int h, int S, int& c0, int& c1, int& c2, int& c3, bool in) {
+    using SH = T14Shape<LEN>;
     if constexpr (MODE == T14_ROWS) {
-        const int tl = c >> 2, q = c & 3;                 // transform within the group, block of 32 lines
-        c0 = 64 * q; c1 = 64 * h; c3 = 0;
-        c2 = (type == 1 && in) ? (grp % S) * 64 + tl : grp * 64 + tl;
+        const int tl = c / SH::TPT, q = c % SH::TPT;      // transform within the group, block of LINES lines
+        c0 = 2 * SH::LINES * q; c1 = (LEN / 2) * h; c3 = 0;
+        c2 = (type == 1 && in) ? (grp % S) * SH::TPP + tl : grp * SH::TPP + tl;
     } else {
-        const int tbl = c >> 7, r = c & 127;              // t-block within the group (2), n2 (pass 1) or k1 (pass 2)
-        if (type == 1 && in) { c0 = 0; c1 = r; c2 = 64 * h; c3 = (grp % S) * 2 + tbl; }
-        else { c0 = 64 * (grp * 2 + tbl); c1 = r; c2 = 64 * h; c3 = 0; }
+        const int tbl = c / LEN, r = c % LEN;             // t-block within the group, n2 (pass 1) or k1 (pass 2)
+        if (type == 1 && in) { c0 = 0; c1 = r; c2 = (LEN / 2) * h; c3 = (grp % S) * SH::TBP + tbl; }
+        else { c0 = 2 * SH::LINES * (grp * SH::TBP + tbl); c1 = r; c2 = (LEN / 2) * h; c3 = 0; }
     }
 }
 
-template <int MODE, bool INV, bool PROF>
+template <int LEN, int MODE, bool INV, bool PROF>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_int,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ Tma14Params a) {
@@ -87,8 +104,10 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     volatile int* log = reinterpret_cast<volatile int*>(bars + 22);        // [32]
     volatile int* log_count = reinterpret_cast<volatile int*>(bars + 38);
     volatile int* ready_sh = reinterpret_cast<volatile int*>(bars + 39);
+    using SH = T14Shape<LEN>;
     constexpr int TPT = 256;                               // tiles per phase
     constexpr int HALF_ELEMS = T14_HALF_BYTES / 16;        // 2048
+    constexpr int T14_LINES = SH::LINES, T14_LEN = LEN, T14_ROWPITCH = SH::ROWPITCH, NJ = SH::NJ, KB = SH::KB;
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
@@ -139,7 +158,7 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     if (token) { mbar_arrive(fb); continue; }
                     mbar_expect_tx(fb, T14_HALF_BYTES);
                     int c0, c1, c2, c3;
-                    t14_coords<MODE>(w.type, w.tf, w.c, h, S, c0, c1, c2, c3, true);
+                    t14_coords<LEN, MODE>(w.type, w.tf, w.c, h, S, c0, c1, c2, c3, true);
                     tma_load_4d(land + (size_t)s * HALF_ELEMS, w.type == 0 ? &tm_x : &tm_int, c0, c1, c2, c3, fb);
                 }
                 if (!tokens && (it & 1)) cur = atomicAdd(a.queue, 2);
@@ -165,7 +184,7 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 const int item = log[it & 31];
                 if (item < 0) break;
                 const TmaItem pi = tma_decode(item, B, D);
-                if (pi.type == 1 && (a.opt & 1)) continue;  // experiment: pass-2 tiles stored by the consumers themselves (nothing staged)
+                if (LEN == 128 && pi.type == 1 && (a.opt & 1)) continue;  // experiment: pass-2 tiles stored by the consumers themselves (nothing staged)
                 long long t0 = 0;
                 if (PROF) t0 = clock64();
                 mbar_wait(staged + g, ns & 1);
@@ -174,10 +193,10 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 const cpx* srcb = work + (size_t)g * T14_WELEMS;
                 if (pi.type == 1) {
                     int c0, c1, c2, c3;
-                    t14_coords<MODE>(1, pi.tf, pi.c, 0, S, c0, c1, c2, c3, false);
+                    t14_coords<LEN, MODE>(1, pi.tf, pi.c, 0, S, c0, c1, c2, c3, false);
                     tma_store_4d(&tm_out, c0, c1, c2, c3, srcb);
                     tma_commit();
-                    t14_coords<MODE>(1, pi.tf, pi.c, 1, S, c0, c1, c2, c3, false);
+                    t14_coords<LEN, MODE>(1, pi.tf, pi.c, 1, S, c0, c1, c2, c3, false);
                     tma_store_4d(&tm_out, c0, c1, c2, c3, srcb + HALF_ELEMS);
                     tma_commit();
                 } else {
@@ -191,16 +210,16 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     cpx* slot = a.scratch + (size_t)(pi.tf % S) * ((size_t)1 << 20);
                     if constexpr (MODE == T14_ROWS) {
                         // Int[t][n2 = 32 q + ell][k1]: 32 rows of 2 KiB, contiguous in memory, 129-element pitch in shared memory
-                        cpx* dst = slot + (size_t)(pi.c >> 2) * 16384 + (size_t)(pi.c & 3) * 32 * T14_LEN;
+                        cpx* dst = slot + (size_t)(pi.c / SH::TPT) * (T14_LEN * T14_LEN) + (size_t)(pi.c % SH::TPT) * T14_LINES * T14_LEN;
 #pragma unroll 1
-                        for (int l = 0; l < 16; l++) bulk_store_1d_hint(dst + l * T14_LEN, srcb + l * T14_ROWPITCH, T14_LEN * 16, pol_last);
+                        for (int l = 0; l < T14_LINES / 2; l++) bulk_store_1d_hint(dst + l * T14_LEN, srcb + l * T14_ROWPITCH, T14_LEN * 16, pol_last);
                         tma_commit();
 #pragma unroll 1
-                        for (int l = 16; l < 32; l++) bulk_store_1d_hint(dst + l * T14_LEN, srcb + l * T14_ROWPITCH, T14_LEN * 16, pol_last);
+                        for (int l = T14_LINES / 2; l < T14_LINES; l++) bulk_store_1d_hint(dst + l * T14_LEN, srcb + l * T14_ROWPITCH, T14_LEN * 16, pol_last);
                         tma_commit();
                     } else {
                         // Int[tb][n2][k1][32 t]: the tile is 64 KiB contiguous
-                        cpx* dst = slot + ((size_t)(pi.c >> 7) * 128 + (size_t)(pi.c & 127)) * (T14_LEN * T14_LINES);
+                        cpx* dst = slot + (size_t)pi.c * (T14_LEN * T14_LINES);
                         bulk_store_1d_hint(dst, srcb, T14_HALF_BYTES, pol_last);
                         tma_commit();
                         bulk_store_1d_hint(dst + HALF_ELEMS, srcb + HALF_ELEMS, T14_HALF_BYTES, pol_last);
@@ -227,7 +246,10 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     const int g = warp >> 2;
-    const int j = warp & 3, ell = tid & 31;                 // point residue mod 4 (warp-uniform), line
+    // LEN = 128: point residue mod 4 = warp (uniform), line = lane; LEN = 256: residue mod 8 = 2 warp + (lane >> 4), line = lane & 15
+    const int j = LEN == 128 ? (warp & 3) : 2 * (warp & 3) + ((tid >> 4) & 1), ell = tid & (T14_LINES - 1);
+    cpx wj = make_double2(1.0, 0.0);                        // LEN = 256: w_256^j, the base of the twiddle chain
+    if constexpr (LEN == 256) wj = __ldg(a.wl + j);
     cpx* wbuf = work + (size_t)g * T14_WELEMS;
     unsigned nrd = 0, nst = 0;
     bool prev_staged = false;                               // the previous tile left staged output in the work buffer (pass 1 only)
@@ -249,7 +271,7 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         {   // points j + 4 i of line ell: rows j + 4 i of the tile, i < 16 in the first half
             const cpx* s = land + (size_t)s0 * HALF_ELEMS + j * T14_LINES + ell;
 #pragma unroll
-            for (int i = 0; i < 16; i++) x[i] = INV ? cconj_if(s[i * 4 * T14_LINES], ld_conj) : s[i * 4 * T14_LINES];
+            for (int i = 0; i < 16; i++) x[i] = INV ? cconj_if(s[i * NJ * T14_LINES], ld_conj) : s[i * NJ * T14_LINES];
         }
         mbar_arrive(freed_h + s0);
         if (PROF) t0 = clock64();
@@ -260,34 +282,40 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         {
             const cpx* s = land + (size_t)s1 * HALF_ELEMS + j * T14_LINES + ell;
 #pragma unroll
-            for (int i = 0; i < 16; i++) x[16 + i] = INV ? cconj_if(s[i * 4 * T14_LINES], ld_conj) : s[i * 4 * T14_LINES];
+            for (int i = 0; i < 16; i++) x[16 + i] = INV ? cconj_if(s[i * NJ * T14_LINES], ld_conj) : s[i * NJ * T14_LINES];
         }
         mbar_arrive(freed_h + s1);
-        dft32(x);                                           // Y_j[k] = sum_i x[j + 4 i] w_32^(i k)
-        if (j != 0) {                                       // warp-uniform: w_128^(j k) from the parameter bank
+        dft32(x);                                           // Y_j[k] = sum_i x[j + NJ i] w_32^(i k)
+        if constexpr (LEN == 128) {
+            if (j != 0) {                                   // warp-uniform: w_128^(j k) from the parameter bank
 #pragma unroll
-            for (int k = 1; k < 32; k++) x[k] = cmul(x[k], a.w128[j - 1][k]);
+                for (int k = 1; k < 32; k++) x[k] = cmul(x[k], a.w128[j - 1][k]);
+            }
+        } else {
+            asm volatile("" : "+d"(wj.x), "+d"(wj.y));
+            mul_powers32(x, wj);                            // w_256^(j k): j differs between the halves of a warp
         }
         if (PROF) t0 = clock64();
         if (prev_staged) mbar_wait(drained + 2 * g, (nst - 1) & 1);
         if (PROF) c_drain += clock64() - t0;
-        // exchange: Y_j[k] -> row 4 k + j of the work buffer, column ell; thread (ell, j') then takes rows 32 j' .. 32 j' + 31,
-        // i.e. k = 8 j' + k_lo, all four j
+        // exchange: Y_j[k] -> row NJ k + j of the work buffer, column ell; thread (ell, j') then takes rows 32 j' .. 32 j' + 31,
+        // i.e. k = KB j' + k_lo, all NJ residues
         {
             cpx* s = wbuf + j * T14_LINES + ell;
 #pragma unroll
-            for (int k = 0; k < 16; k++) s[k * 4 * T14_LINES] = x[k];                        // rows < 64
+            for (int k = 0; k < 16; k++) s[k * NJ * T14_LINES] = x[k];                       // rows < LEN / 2
             if (PROF) t0 = clock64();
             if (prev_staged) mbar_wait(drained + 2 * g + 1, (nst - 1) & 1);
             if (PROF) c_drain += clock64() - t0;
 #pragma unroll
-            for (int k = 16; k < 32; k++) s[k * 4 * T14_LINES] = x[k];
+            for (int k = 16; k < 32; k++) s[k * NJ * T14_LINES] = x[k];
         }
-        // four-step twiddle bases of this line (pass 1): w^(n2 * 8 j'), w^(n2), w^(32 n2)
+        // four-step twiddle bases of this line (pass 1): w^(n2 * KB j'), w^(n2), w^(32 n2)
         cpx tb0, tb1, tb32;
         if (wi.type == 0) {
-            const unsigned n2 = MODE == T14_ROWS ? (unsigned)((wi.c & 3) * 32 + ell) : (unsigned)(wi.c & 127);
-            const unsigned e0 = (n2 * 8u * (unsigned)j) & 16383u, e1 = n2 & 16383u, e32 = (n2 * 32u) & 16383u;
+            constexpr unsigned NMASK = (unsigned)(LEN * LEN - 1);
+            const unsigned n2 = MODE == T14_ROWS ? (unsigned)((wi.c % SH::TPT) * T14_LINES + ell) : (unsigned)(wi.c % LEN);
+            const unsigned e0 = (n2 * (unsigned)KB * (unsigned)j) & NMASK, e1 = n2 & NMASK, e32 = (n2 * 32u) & NMASK;
             tb0 = cmul(__ldg(a.tw_hi + (e0 >> 12)), __ldg(a.tw_lo + (e0 & 4095u)));
             tb1 = cmul(__ldg(a.tw_hi + (e1 >> 12)), __ldg(a.tw_lo + (e1 & 4095u)));
             tb32 = cmul(__ldg(a.tw_hi + (e32 >> 12)), __ldg(a.tw_lo + (e32 & 4095u)));
@@ -299,53 +327,56 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         {
             const cpx* s = wbuf + (32 * j) * T14_LINES + ell;
 #pragma unroll
-            for (int r = 0; r < 32; r++) x[r] = s[r * T14_LINES];                            // x[4 k_lo + jj] = Y_jj[8 j + k_lo]
+            for (int r = 0; r < 32; r++) x[r] = s[r * T14_LINES];                            // x[NJ k_lo + jj] = Y_jj[KB j + k_lo]
         }
         mbar_arrive(rd + g);
 #pragma unroll
-        for (int kl = 0; kl < 8; kl++) dft4<1>(&x[4 * kl]);                                  // x[4 k_lo + m] = X[8 j + k_lo + 32 m]
+        for (int kl = 0; kl < KB; kl++) {                                                    // x[NJ k_lo + m] = X[KB j + k_lo + 32 m]
+            if constexpr (NJ == 4) dft4<1>(&x[4 * kl]);
+            else dft8_fma<1>(&x[8 * kl]);
+        }
         if (PROF) t0 = clock64();
         mbar_wait(rd + g, nrd & 1);                         // every gather of this tile is done: the buffer may be overwritten
         nrd++;
         if (PROF) c_rd += clock64() - t0;
         if (wi.type == 0) {
-            // x[4 k_lo + m] *= w^(n2 (8 j + k_lo + 32 m)) = tb0 * tb1^k_lo * tb32^m
-            cpx c[8];
+            // x[NJ k_lo + m] *= w^(n2 (KB j + k_lo + 32 m)) = tb0 * tb1^k_lo * tb32^m
+            cpx c[KB];
             c[0] = tb0;
 #pragma unroll
-            for (int kl = 1; kl < 8; kl++) c[kl] = cmul(c[kl - 1], tb1);
+            for (int kl = 1; kl < KB; kl++) c[kl] = cmul(c[kl - 1], tb1);
 #pragma unroll
-            for (int m = 0; m < 4; m++) {
+            for (int m = 0; m < NJ; m++) {
 #pragma unroll
-                for (int kl = 0; kl < 8; kl++) {
-                    x[4 * kl + m] = cmul(x[4 * kl + m], c[kl]);
-                    if (m < 3) c[kl] = cmul(c[kl], tb32);
+                for (int kl = 0; kl < KB; kl++) {
+                    x[NJ * kl + m] = cmul(x[NJ * kl + m], c[kl]);
+                    if (m < NJ - 1) c[kl] = cmul(c[kl], tb32);
                 }
             }
             if constexpr (MODE == T14_ROWS) {
-                cpx* s = wbuf + ell * T14_ROWPITCH + 8 * j;  // Int[n2 = line][k1 = 8 j + k_lo + 32 m]
+                cpx* s = wbuf + ell * T14_ROWPITCH + KB * j; // Int[n2 = line][k1 = KB j + k_lo + 32 m]
 #pragma unroll
-                for (int kl = 0; kl < 8; kl++)
+                for (int kl = 0; kl < KB; kl++)
 #pragma unroll
-                    for (int m = 0; m < 4; m++) s[kl + 32 * m] = x[4 * kl + m];
+                    for (int m = 0; m < NJ; m++) s[kl + 32 * m] = x[NJ * kl + m];
             } else {
-                cpx* s = wbuf + (8 * j) * T14_LINES + ell;   // Int[k1][32 t]: row k1, column = line
+                cpx* s = wbuf + (KB * j) * T14_LINES + ell;  // Int[k1][LINES t]: row k1, column = line
 #pragma unroll
-                for (int kl = 0; kl < 8; kl++)
+                for (int kl = 0; kl < KB; kl++)
 #pragma unroll
-                    for (int m = 0; m < 4; m++) s[(kl + 32 * m) * T14_LINES] = x[4 * kl + m];
+                    for (int m = 0; m < NJ; m++) s[(kl + 32 * m) * T14_LINES] = x[NJ * kl + m];
             }
             fence_proxy_async();
             mbar_arrive(staged + g);
             nst++;
             prev_staged = true;
-        } else if (!(a.opt & 1)) {
-            cpx* s = wbuf + (8 * j) * T14_LINES + ell;       // X[k2 = 8 j + k_lo + 32 m]: row k2 of the tile, column = line
+        } else if (LEN != 128 || !(a.opt & 1)) {
+            cpx* s = wbuf + (KB * j) * T14_LINES + ell;      // X[k2 = KB j + k_lo + 32 m]: row k2 of the tile, column = line
 #pragma unroll
-            for (int kl = 0; kl < 8; kl++)
+            for (int kl = 0; kl < KB; kl++)
 #pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    const cpx v = x[4 * kl + m];
+                for (int m = 0; m < NJ; m++) {
+                    const cpx v = x[NJ * kl + m];
                     s[(kl + 32 * m) * T14_LINES] = INV ? make_double2(v.x, -v.y) : v;
                 }
             fence_proxy_async();

@@ -1,164 +1,16 @@
-// Host side of the TMA-fed fused four-step for 2^14-point transforms (fft_tma14.cuh): rows of a batch or columns of a
-// row-major matrix; tensor maps, scratch slots under a persisting L2 window, dependency counters, one persistent launch
-// per up to 512 phases.
-#include <math.h>
-#include <string.h>
-#include "engine.h"
-#include "fft_tma14.cuh"
+// 2^14-point transforms (N = 128 x 128) through the TMA-fed fused four-step: instantiations and entry points (tma14_host.cuh)
+#include "tma14_host.cuh"
 
 namespace gd {
 
-static Status invalid14(const char* msg) { set_error(msg); return GD_ERR_INVALID; }
-
-typedef CUresult (*TmaEncodeFn14)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static Status encoder14(TmaEncodeFn14* out) {
-    static TmaEncodeFn14 fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        GD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        if (!p || q != cudaDriverEntryPointSuccess) return invalid14("cuTensorMapEncodeTiled is not available in this driver");
-        fn = (TmaEncodeFn14)p;
-    }
-    *out = fn;
-    return GD_OK;
-}
-
-// rank-4 map over doubles: dims d0..d3 (d0 in doubles), byte strides s1..s3 of dims 1..3, box b0..b3
-static Status map4(TmaEncodeFn14 enc, const void* base, const cuuint64_t (&dims)[4], const cuuint64_t (&strides)[3], const cuuint32_t (&box)[4],
-                   CUtensorMap* m) {
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return invalid14("cuTensorMapEncodeTiled failed (2^14 fused kernel: pointer alignment or pitch?)");
-    return GD_OK;
-}
-
 bool tma14_rows_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, long long batch, int ld_conj, int st_conj,
                            double scale) {
-    const bool fwd = !ld_conj && !st_conj && scale == 1.0, inv = ld_conj && st_conj;
-    return (fwd || inv) && batch >= 128 && batch % 64 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && in_dist >= 16384 &&
-           out_dist >= 16384 && in_dist < (1LL << 35) && out_dist < (1LL << 35);
+    return tma2d_rows_applicable<128>(in, in_dist, out, out_dist, batch, ld_conj, st_conj, scale);
 }
-bool tma14_cols_applicable(const cpx* src, const cpx* dst, long long len, long long s) {
-    return len == 16384 && s >= 128 && s % 64 == 0 && s < (1LL << 30) && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
-}
-
-template <int MODE, bool INV, bool PROF = false>
-static cudaError_t launch14(int grid, const CUtensorMap& mx, const CUtensorMap& mi, const CUtensorMap& mo, const Tma14Params& f, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(fft_tma14_kernel<MODE, INV, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, T14_SMEM);   // per device
-    if (e != cudaSuccess) return e;
-    fft_tma14_kernel<MODE, INV, PROF><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f);
-    return cudaGetLastError();
-}
-
-// mode ROWS: `count` transforms of 2^14 points, transform t at in + t * in_dist / out + t * out_dist (count % 64 == 0).
-// mode COLS: the 2^14 rows of a row-major matrix with `count` columns (count % 64 == 0): every column is a transform;
-//            in_dist / out_dist are ignored (row pitch = count).
+bool tma14_cols_applicable(const cpx* src, const cpx* dst, long long len, long long s) { return tma2d_cols_applicable<128>(src, dst, len, s); }
 Status fft_tma_2p14(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
                     cudaStream_t st) {
-    TmaEncodeFn14 enc;
-    GD_TRY(encoder14(&enc));
-    const int S = d.tma_slots;
-    const int D = d.tma_delay < S - 1 ? d.tma_delay : S - 1;
-    TwiddleTable tw;
-    GD_TRY(d.twiddles(14, &tw));
-    cpx* scratch;
-    const size_t slot_elems = (size_t)1 << 20, scr_bytes = (size_t)S * slot_elems * sizeof(cpx);
-    GD_TRY(d.ensure_scratch(SCR_TMA, scr_bytes, (void**)&scratch));
-    const long long CH = 512;
-    int* cnt;
-    GD_TRY(d.ensure_scratch(SCR_CNT, (2 * (size_t)CH + 2) * sizeof(int), (void**)&cnt));
-    CUtensorMap m_int;
-    if (mode == T14_ROWS) {
-        const cuuint64_t dims[4] = {256, 128, (cuuint64_t)(64 * S), 1};
-        const cuuint64_t str[3] = {2048, 16384 * 16, (cuuint64_t)16384 * 16 * 64 * S};
-        const cuuint32_t box[4] = {64, 64, 1, 1};
-        GD_TRY(map4(enc, scratch, dims, str, box, &m_int));
-    } else {
-        const cuuint64_t dims[4] = {64, 128, 128, (cuuint64_t)(2 * S)};
-        const cuuint64_t str[3] = {512, 65536, 8388608};
-        const cuuint32_t box[4] = {64, 1, 64, 1};
-        GD_TRY(map4(enc, scratch, dims, str, box, &m_int));
-    }
-    Tma14Params f;
-    memset(&f, 0, sizeof(f));
-    for (int j = 1; j < 4; j++)
-        for (int k = 0; k < 32; k++) {
-            const int e = (j * k) % 128;
-            long double c = 1, s = 0;
-            if (e == 0) { c = 1; s = 0; } else if (e == 32) { c = 0; s = 1; } else if (e == 64) { c = -1; s = 0; } else if (e == 96) { c = 0; s = -1; }
-            else { const long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)e / 128.0L; c = cosl(ang); s = sinl(ang); }
-            f.w128[j - 1][k] = make_double2((double)c, (double)(-s));
-        }
-    const bool window = d.use_l2_window && d.l2_persist_max > 0 && d.l2_window_max > 0;
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
-    if (window) {
-        size_t want = scr_bytes < d.l2_persist_max ? scr_bytes : d.l2_persist_max;
-        if (d.l2_carved != want) {
-            GD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-            d.l2_carved = want;
-        }
-        attr.accessPolicyWindow.base_ptr = scratch;
-        attr.accessPolicyWindow.num_bytes = scr_bytes < d.l2_window_max ? scr_bytes : d.l2_window_max;
-        double ratio = (double)d.l2_carved / (double)attr.accessPolicyWindow.num_bytes;
-        attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        GD_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
-        d.l2_dirty = true;
-    }
-    Status rc = GD_OK;
-    const long long groups = count / 64;
-    for (long long g0 = 0; g0 < groups && rc == GD_OK; g0 += CH) {
-        const long long ng = groups - g0 < CH ? groups - g0 : CH;
-        CUtensorMap m_x, m_out;
-        if (mode == T14_ROWS) {
-            const cuuint64_t dims[4] = {256, 128, (cuuint64_t)(ng * 64), 1};
-            const cuuint32_t box[4] = {64, 64, 1, 1};
-            const cuuint64_t sx[3] = {2048, (cuuint64_t)in_dist * 16, (cuuint64_t)in_dist * 16 * (cuuint64_t)(ng * 64)};
-            const cuuint64_t so[3] = {2048, (cuuint64_t)out_dist * 16, (cuuint64_t)out_dist * 16 * (cuuint64_t)(ng * 64)};
-            if ((rc = map4(enc, in + g0 * 64 * in_dist, dims, sx, box, &m_x)) != GD_OK) break;
-            if ((rc = map4(enc, out + g0 * 64 * out_dist, dims, so, box, &m_out)) != GD_OK) break;
-        } else {
-            const cuuint64_t dims[4] = {(cuuint64_t)(2 * ng * 64), 128, 128, 1};
-            const cuuint32_t box[4] = {64, 1, 64, 1};
-            const cuuint64_t str[3] = {(cuuint64_t)count * 16, (cuuint64_t)count * 16 * 128, (cuuint64_t)count * 16 * 128 * 128};
-            if ((rc = map4(enc, in + g0 * 64, dims, str, box, &m_x)) != GD_OK) break;
-            if ((rc = map4(enc, out + g0 * 64, dims, str, box, &m_out)) != GD_OK) break;
-        }
-        f.batch = (int)ng; f.delay = D; f.nslots = S; f.scratch = scratch;
-        f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
-        f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.scale = scale;
-        f.out = mode == T14_ROWS ? out + g0 * 64 * out_dist : out + g0 * 64;
-        f.out_dist = mode == T14_ROWS ? out_dist : count;
-        f.opt = d.tma_opt >> 4;
-        f.prof = nullptr;
-        if (d.tma_prof) {
-            long long* pr;
-            GD_TRY(d.ensure_scratch(SCR_PROF, (size_t)d.num_sms * TMA_PROF_SLOTS * sizeof(long long), (void**)&pr));
-            GD_CUDA(cudaMemsetAsync(pr, 0, (size_t)d.num_sms * TMA_PROF_SLOTS * sizeof(long long), st));
-            f.prof = pr;
-        }
-        cudaError_t e = cudaMemsetAsync(cnt, 0, (2 * (size_t)CH + 2) * sizeof(int), st);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(counters)"); break; }
-        const long long nitems = 2 * ng * 256;
-        const int grid = (int)(nitems < d.num_sms ? nitems : d.num_sms);
-        if (f.prof && !inv) e = mode == T14_ROWS ? launch14<T14_ROWS, false, true>(grid, m_x, m_int, m_out, f, st) : launch14<T14_COLS, false, true>(grid, m_x, m_int, m_out, f, st);
-        else if (mode == T14_ROWS) e = inv ? launch14<T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
-        else e = inv ? launch14<T14_COLS, true>(grid, m_x, m_int, m_out, f, st) : launch14<T14_COLS, false>(grid, m_x, m_int, m_out, f, st);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "fft_tma14_kernel launch"); break; }
-        g_launches++;
-    }
-    if (window) {
-        attr.accessPolicyWindow.num_bytes = 0;
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-    }
-    return rc;
+    return fft_tma_2d<128>(d, mode, in, in_dist, out, out_dist, count, inv, scale, st);
 }
 
 }  // namespace gd

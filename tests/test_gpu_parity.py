@@ -356,6 +356,54 @@ def test_fft2_fused_2p14_lines(gd, rows, cols):  # the fused 2^14 kernel (fft_tm
     assert np.array_equal(o3, out) and np.array_equal(b3, back)
 
 
+@pytest.mark.parametrize("rows,cols", [(65536, 32), (32, 65536), (65536, 80), (48, 65536)])
+def test_fft2_fused_2p16_lines(gd, rows, cols):  # the same kernel with 256-point sub-lines: columns of a 2^16-row matrix, batched 2^16 rows
+    _, capi, L = gd
+    x = oracle.splitmix_complex(rows * cols, 4).reshape(rows, cols)
+    out, back = np.empty_like(x), np.empty_like(x)
+    l0 = L.gd_kernel_launches()
+    capi.check(L.gd_fft2_c2c(x.ctypes.data, out.ctypes.data, rows, cols, 1))
+    fused_launches = L.gd_kernel_launches() - l0
+    assert rel_l2(out, oracle.fft2(x)) <= TOL
+    capi.check(L.gd_fft2_c2c(out.ctypes.data, back.ctypes.data, rows, cols, -1))
+    assert rel_l2(back, x) <= TOL
+    capi.check(L.gd_set_option(b"tma16", 0))     # and the two-launch schedule gives the same result with more launches
+    try:
+        o2 = np.empty_like(x)
+        l0 = L.gd_kernel_launches()
+        capi.check(L.gd_fft2_c2c(x.ctypes.data, o2.ctypes.data, rows, cols, 1))
+        assert L.gd_kernel_launches() - l0 > fused_launches
+    finally:
+        capi.check(L.gd_set_option(b"tma16", 1))
+    assert rel_l2(o2, out) <= 1e-14
+
+
+def test_tma16_fused_stress(gd):                  # race hunt for the 256 x 256 variant, both modes (Parseval per line)
+    _, capi, L = gd
+    import torch
+    n, nb, reps = 1 << 16, 512, 25
+    x = torch.empty(nb * n * 2, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), nb * n * 2, 3, 0, None))
+    capi.check(L.gd_stream_sync(None))
+    xc = torch.view_as_complex(x.view(-1, 2))
+    ex_rows = (xc.view(nb, n).abs() ** 2).sum(1)
+    ex_cols = (xc.view(n, nb).abs() ** 2).sum(0)
+    for _ in range(reps):
+        y.zero_()
+        torch.cuda.synchronize()
+        capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, nb, 1, None))
+        capi.check(L.gd_stream_sync(None))
+        ey = (torch.view_as_complex(y.view(-1, 2)).view(nb, n).abs() ** 2).sum(1)
+        assert float(((ey / n - ex_rows).abs() / ex_rows).max()) < 1e-13
+        y.zero_()
+        torch.cuda.synchronize()
+        capi.check(L.gd_fft_strided_c2c_dev(x.data_ptr(), y.data_ptr(), 1, n, nb, 1, None))
+        capi.check(L.gd_stream_sync(None))
+        ey = (torch.view_as_complex(y.view(-1, 2)).view(n, nb).abs() ** 2).sum(0)
+        assert float(((ey / n - ex_cols).abs() / ex_cols).max()) < 1e-13
+
+
 def test_fft2_16384_square_sampled(gd):          # config C3: the full 16384 x 16384 matrix, device resident
     """Output rows / columns of the full-size result against oracle.fft of the matching single-bin DFT of the other axis
     (a float64 matrix-vector product with exactly reduced phasors, computed by torch -- not by this library):
