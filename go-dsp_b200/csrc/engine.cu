@@ -20,16 +20,29 @@ bool tma_fused_applicable(const void* in, long long in_dist, const cpx* out, lon
 Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long batch, int ld_conj,
                     int st_conj, double scale, cudaStream_t st);
 int pass32_tile_lines(int variant);
-bool tma14_rows_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, long long batch, int ld_conj, int st_conj,
-                           double scale);
-bool tma14_cols_applicable(const cpx* src, const cpx* dst, long long len, long long s);
-Status fft_tma_2p14(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
-                    cudaStream_t st);
-bool tma16_rows_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, long long batch, int ld_conj, int st_conj,
-                           double scale);
-bool tma16_cols_applicable(const cpx* src, const cpx* dst, long long len, long long s);
-Status fft_tma_2p16(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
-                    cudaStream_t st);
+// fused TMA four-step for 2^13 .. 2^18 points (fft_tma14.cuh; one translation unit per size)
+#define GD_TMA2D_DECL(LG)                                                                                                                \
+    bool tma##LG##_rows_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, long long batch, int ld_conj,  \
+                                   int st_conj, double scale);                                                                           \
+    bool tma##LG##_cols_applicable(const cpx* src, const cpx* dst, long long len, long long ncols, long long pitch);                     \
+    Status fft_tma_2p##LG(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, \
+                          double scale, cudaStream_t st);
+GD_TMA2D_DECL(13) GD_TMA2D_DECL(14) GD_TMA2D_DECL(15) GD_TMA2D_DECL(16) GD_TMA2D_DECL(17) GD_TMA2D_DECL(18)
+struct Tma2dEntry {
+    bool (*rows_ok)(const void*, long long, const cpx*, long long, long long, int, int, double);
+    bool (*cols_ok)(const cpx*, const cpx*, long long, long long, long long);
+    Status (*run)(Device&, int, const cpx*, long long, cpx*, long long, long long, bool, double, cudaStream_t);
+    int unit;                                            // transforms / columns per phase: 2^20 / N
+};
+static const Tma2dEntry* tma2d_entry(const Device& d, int log2n) {
+    static const Tma2dEntry tab[6] = {
+        {tma13_rows_applicable, tma13_cols_applicable, fft_tma_2p13, 128}, {tma14_rows_applicable, tma14_cols_applicable, fft_tma_2p14, 64},
+        {tma15_rows_applicable, tma15_cols_applicable, fft_tma_2p15, 32},  {tma16_rows_applicable, tma16_cols_applicable, fft_tma_2p16, 16},
+        {tma17_rows_applicable, tma17_cols_applicable, fft_tma_2p17, 8},   {tma18_rows_applicable, tma18_cols_applicable, fft_tma_2p18, 4}};
+    if (!d.use_tma || log2n < 13 || log2n > 18) return nullptr;
+    if (log2n == 14 ? !d.use_tma14 : !d.use_tma16) return nullptr;       // "tma14": the 2^14 kernel; "tma16": every other size of the family
+    return &tab[log2n - 13];
+}
 
 // ------------------------------------------------------------------ errors
 std::atomic<long long> g_launches{0};
@@ -314,17 +327,16 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         if (tma_fused_applicable(in, in_dist, out, out_dist, lc, sc, scl))
             return fft_tma_2p20(d, (const cpx*)in, in_dist, out, out_dist, batch, lc, sc, scl, st);
     }
-    if (d.use_tma && d.use_tma14 && lean && log2n == 14 && !d.debug_alias) {
+    if (const Tma2dEntry* te = (lean && !d.debug_alias) ? tma2d_entry(d, log2n) : nullptr) {
+        // 2^13 .. 2^18: whole phases of the batch through the fused kernel, a remainder of less than one phase through the chunks below
         const int lc = (ops.ld_flags & LD_CONJ) ? 1 : 0, sc = (ops.st_flags & ST_CONJ) ? 1 : 0;
         const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
-        if (tma14_rows_applicable(in, in_dist, out, out_dist, batch, lc, sc, scl))
-            return fft_tma_2p14(d, 0, (const cpx*)in, in_dist, out, out_dist, batch, lc != 0, scl, st);
-    }
-    if (d.use_tma && d.use_tma16 && lean && log2n == 16 && !d.debug_alias) {
-        const int lc = (ops.ld_flags & LD_CONJ) ? 1 : 0, sc = (ops.st_flags & ST_CONJ) ? 1 : 0;
-        const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
-        if (tma16_rows_applicable(in, in_dist, out, out_dist, batch, lc, sc, scl))
-            return fft_tma_2p16(d, 0, (const cpx*)in, in_dist, out, out_dist, batch, lc != 0, scl, st);
+        const long long main = batch - batch % te->unit;
+        if (main > 0 && te->rows_ok(in, in_dist, out, out_dist, main, lc, sc, scl)) {
+            GD_TRY(te->run(d, 0, (const cpx*)in, in_dist, out, out_dist, main, lc != 0, scl, st));
+            if (main == batch) return GD_OK;
+            return fft_pow2(d, (const cpx*)in + main * in_dist, in_dist, out + main * out_dist, out_dist, log2n, batch - main, ops, st);
+        }
     }
     if (d.use_fused && lean && (log2n % 2) == 0 && log2n >= 16 && batch * (2LL << (log2n / 2)) < (1LL << 30)) {
         // both passes in one persistent kernel, intermediate resident in L2 (fft_fused.cuh)
@@ -961,17 +973,17 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
     }
     if (sub && !(is_pow2(len) && len > 4096 && len <= (1LL << 24) && (double)len * (double)s < 2147483648.0))
         return invalid("fft_axis: a column range needs a power-of-two length in (4096, 2^24]");
-    if (!sub && d.use_tma && d.use_tma14 && tma14_cols_applicable(src, dst, len, s)) {
-        // every column of a 2^14-row matrix: one fused launch, intermediate resident in L2 (fft_tma14.cuh)
-        for (long long o = 0; o < outer; o++)
-            GD_TRY(fft_tma_2p14(d, 1, src + o * len * s, 0, dst + o * len * s, 0, s, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
-        return GD_OK;
-    }
-    if (!sub && d.use_tma && d.use_tma16 && tma16_cols_applicable(src, dst, len, s)) {
-        // every column of a 2^16-row matrix (the line passes of the sharded 2^32-point transform): same kernel, 256 x 256
-        for (long long o = 0; o < outer; o++)
-            GD_TRY(fft_tma_2p16(d, 1, src + o * len * s, 0, dst + o * len * s, 0, s, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
-        return GD_OK;
+    if (const Tma2dEntry* te = (!sub && p2) ? tma2d_entry(d, ilog2ll(len)) : nullptr) {
+        // columns of a matrix with 2^13 .. 2^17 rows (2^14: fft.FFT2 on 16384 x 16384; 2^16: the line passes of the sharded
+        // 2^32-point transform): whole phases of columns in one fused launch, intermediate resident in L2 (fft_tma14.cuh);
+        // a remainder of less than one phase of columns goes through the column-range path below
+        const long long main = s - s % te->unit;
+        if (main > 0 && te->cols_ok(src, dst, len, main, s)) {
+            for (long long o = 0; o < outer; o++)
+                GD_TRY(te->run(d, 1, src + o * len * s, s, dst + o * len * s, s, main, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
+            if (main == s) return GD_OK;
+            return fft_axis(d, src, dst, outer, len, s, dir, st, main, s - main);
+        }
     }
     if (p2 && len <= (1LL << 24) && fits31) {
         // strided four-step on blocks of cb adjacent columns; the inter-pass block [len][cb] stays in L2

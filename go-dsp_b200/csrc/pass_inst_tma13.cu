@@ -1,0 +1,6 @@
+// 2^13-point transforms (N = 128 x 64) through the TMA-fed fused four-step (fft_tma14.cuh): instantiations and entry points
+#include "tma14_host.cuh"
+
+namespace gd {
+GD_TMA2D_ENTRY(13, 128, 64)
+}  // namespace gd

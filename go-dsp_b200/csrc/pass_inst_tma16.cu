@@ -1,16 +1,6 @@
-// 2^16-point transforms (N = 256 x 256) through the TMA-fed fused four-step: instantiations and entry points (tma14_host.cuh)
+// 2^16-point transforms (N = 256 x 256) through the TMA-fed fused four-step (fft_tma14.cuh): instantiations and entry points
 #include "tma14_host.cuh"
 
 namespace gd {
-
-bool tma16_rows_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, long long batch, int ld_conj, int st_conj,
-                           double scale) {
-    return tma2d_rows_applicable<256>(in, in_dist, out, out_dist, batch, ld_conj, st_conj, scale);
-}
-bool tma16_cols_applicable(const cpx* src, const cpx* dst, long long len, long long s) { return tma2d_cols_applicable<256>(src, dst, len, s); }
-Status fft_tma_2p16(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
-                    cudaStream_t st) {
-    return fft_tma_2d<256>(d, mode, in, in_dist, out, out_dist, count, inv, scale, st);
-}
-
+GD_TMA2D_ENTRY(16, 256, 256)
 }  // namespace gd

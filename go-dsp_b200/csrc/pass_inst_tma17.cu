@@ -1,0 +1,6 @@
+// 2^17-point transforms (N = 512 x 256) through the TMA-fed fused four-step (fft_tma14.cuh): instantiations and entry points
+#include "tma14_host.cuh"
+
+namespace gd {
+GD_TMA2D_ENTRY(17, 512, 256)
+}  // namespace gd

@@ -1,6 +1,6 @@
-// Host side of the TMA-fed fused four-step for 2^14- and 2^16-point transforms (fft_tma14.cuh, N = LEN x LEN with LEN = 128
-// or 256): rows of a batch or columns of a row-major matrix; tensor maps, scratch slots under a persisting L2 window,
-// dependency counters, one persistent launch per up to 512 phases. Included by one translation unit per LEN.
+// Host side of the TMA-fed fused four-step for 2^13- .. 2^18-point transforms (fft_tma14.cuh, N = LA x LB): rows of a batch
+// or columns of a row-major matrix; tensor maps, scratch slots under a persisting L2 window, dependency counters, one
+// persistent launch per up to 512 phases. Included by one translation unit per size (pass_inst_tma<log2 N>.cu).
 #pragma once
 #include <math.h>
 #include <string.h>
@@ -38,38 +38,41 @@ static Status map4(TmaEncodeFn14 enc, const void* base, const cuuint64_t (&dims)
     return GD_OK;
 }
 
-template <int LEN>
+template <int LA, int LB>
 static bool tma2d_rows_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, long long batch, int ld_conj, int st_conj,
                                   double scale) {
-    using SH = T14Shape<LEN>;
-    const long long N = (long long)LEN * LEN;
+    using SH = T14Shape<LA, LB>;
+    const long long N = SH::N;
     const bool fwd = !ld_conj && !st_conj && scale == 1.0, inv = ld_conj && st_conj;
-    return (fwd || inv) && batch >= 2 * SH::TPP && batch % SH::TPP == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && in_dist >= N &&
+    return (fwd || inv) && batch >= 2 * SH::UNIT && batch % SH::UNIT == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && in_dist >= N &&
            out_dist >= N && in_dist < (1LL << 35) && out_dist < (1LL << 35);
 }
-template <int LEN>
-static bool tma2d_cols_applicable(const cpx* src, const cpx* dst, long long len, long long s) {
-    using SH = T14Shape<LEN>;
-    return len == (long long)LEN * LEN && s >= 2 * SH::CPP && s % SH::CPP == 0 && s < (1LL << 30) && ((uintptr_t)src % 16) == 0 &&
-           ((uintptr_t)dst % 16) == 0;
+// columns [0, ncols) of a row-major matrix with N rows and row pitch `pitch`
+template <int LA, int LB>
+static bool tma2d_cols_applicable(const cpx* src, const cpx* dst, long long len, long long ncols, long long pitch) {
+    using SH = T14Shape<LA, LB>;
+    return LB <= 256 && len == (long long)SH::N && ncols >= 2 * SH::UNIT && ncols % SH::UNIT == 0 && pitch >= ncols && pitch < (1LL << 30) &&
+           ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
 }
 
-template <int LEN, int MODE, bool INV, bool PROF = false>
+template <int LA, int LB, int MODE, bool INV, bool PROF = false>
 static cudaError_t launch14(int grid, const CUtensorMap& mx, const CUtensorMap& mi, const CUtensorMap& mo, const Tma14Params& f, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(fft_tma14_kernel<LEN, MODE, INV, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, T14_SMEM);   // per device
+    cudaError_t e = cudaFuncSetAttribute(fft_tma14_kernel<LA, LB, MODE, INV, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, T14_SMEM);   // per device
     if (e != cudaSuccess) return e;
-    fft_tma14_kernel<LEN, MODE, INV, PROF><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f);
+    fft_tma14_kernel<LA, LB, MODE, INV, PROF><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f);
     return cudaGetLastError();
 }
 
-// mode ROWS: `count` transforms of N = LEN^2 points, transform t at in + t * in_dist / out + t * out_dist (count % TPP == 0).
-// mode COLS: the N rows of a row-major matrix with `count` columns (count % CPP == 0): every column is a transform;
-//            in_dist / out_dist are ignored (row pitch = count).
-template <int LEN>
+static inline cuuint64_t clamp_stride(unsigned long long v) { return v < (1ULL << 39) ? v : (1ULL << 39); }   // stride of a dimension of extent 1
+
+// mode ROWS: `count` transforms of N = LA * LB points, transform t at in + t * in_dist / out + t * out_dist (count % UNIT == 0).
+// mode COLS: the first `count` columns of a row-major matrix with N rows (count % UNIT == 0): every column is a transform;
+//            in_dist = out_dist = the row pitch of the matrix in elements.
+template <int LA, int LB>
 static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
                          cudaStream_t st) {
-    using SH = T14Shape<LEN>;
-    constexpr cuuint64_t L = LEN, LINES = SH::LINES, N = (cuuint64_t)LEN * LEN;
+    using SH = T14Shape<LA, LB>;
+    constexpr cuuint64_t A = LA, Bq = LB, N = SH::N, LNA = SH::LINES_A, LNB = SH::LINES_B, UNIT = SH::UNIT;
     TmaEncodeFn14 enc;
     GD_TRY(encoder14(&enc));
     const int S = d.tma_slots;
@@ -84,22 +87,22 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
     GD_TRY(d.ensure_scratch(SCR_CNT, (2 * (size_t)CH + 2) * sizeof(int), (void**)&cnt));
     CUtensorMap m_int;
     if (mode == T14_ROWS) {
-        // Int[t][n2][k1], t < TPP * S: dims (k1 in doubles... the tile box is LINES adjacent elements of a row x LEN / 2 rows
-        const cuuint64_t dims[4] = {2 * L, L, (cuuint64_t)(SH::TPP * S), 1};
-        const cuuint64_t str[3] = {L * 16, N * 16, N * 16 * (cuuint64_t)(SH::TPP * S)};
-        const cuuint32_t box[4] = {(cuuint32_t)(2 * LINES), (cuuint32_t)(L / 2), 1, 1};
+        // Int[t][n2][k1], t < UNIT * S: a pass-2 tile is LINES_B adjacent k1 x LB / 2 rows n2 per half
+        const cuuint64_t dims[4] = {2 * A, Bq, UNIT * (cuuint64_t)S, 1};
+        const cuuint64_t str[3] = {A * 16, N * 16, clamp_stride(N * 16 * UNIT * (cuuint64_t)S)};
+        const cuuint32_t box[4] = {(cuuint32_t)(2 * LNB), (cuuint32_t)(Bq / 2), 1, 1};
         GD_TRY(map4(enc, scratch, dims, str, box, &m_int));
     } else {
-        // Int[tb][n2][k1][LINES t], tb < TBP * S
-        const cuuint64_t dims[4] = {2 * LINES, L, L, (cuuint64_t)(SH::TBP * S)};
-        const cuuint64_t str[3] = {LINES * 16, LINES * 16 * L, LINES * 16 * L * L};
-        const cuuint32_t box[4] = {(cuuint32_t)(2 * LINES), 1, (cuuint32_t)(L / 2), 1};
+        // Int[tb][n2][k1][LINES_A t], tb < TBP * S: a pass-2 tile is RA adjacent k1 x LINES_A columns x LB / 2 rows n2 per half
+        const cuuint64_t dims[4] = {2 * LNA, A, Bq, (cuuint64_t)(SH::TBP * S)};
+        const cuuint64_t str[3] = {LNA * 16, LNA * 16 * A, LNA * 16 * A * Bq};
+        const cuuint32_t box[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)SH::RA, (cuuint32_t)(Bq / 2), 1};
         GD_TRY(map4(enc, scratch, dims, str, box, &m_int));
     }
     Tma14Params f;
     memset(&f, 0, sizeof(f));
-    f.wl = LEN == 256 ? d.wl[8] : nullptr;
-    for (int j = 1; j < 4 && LEN == 128; j++)
+    f.wla = d.wl[T14Len<LA>::LOG2]; f.wlb = d.wl[T14Len<LB>::LOG2];
+    for (int j = 1; j < 4; j++)
         for (int k = 0; k < 32; k++) {
             const int e = (j * k) % 128;
             long double c = 1, s = 0;
@@ -126,31 +129,30 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         d.l2_dirty = true;
     }
     Status rc = GD_OK;
-    const long long UNIT = mode == T14_ROWS ? SH::TPP : SH::CPP;      // transforms / columns per phase
-    const long long groups = count / UNIT;
+    const long long groups = count / (long long)UNIT;
     for (long long g0 = 0; g0 < groups && rc == GD_OK; g0 += CH) {
         const long long ng = groups - g0 < CH ? groups - g0 : CH;
+        const cuuint64_t nt = (cuuint64_t)ng * UNIT;                   // transforms / columns of this launch
         CUtensorMap m_x, m_out;
         if (mode == T14_ROWS) {
-            const cuuint64_t dims[4] = {2 * L, L, (cuuint64_t)(ng * UNIT), 1};
-            const cuuint32_t box[4] = {(cuuint32_t)(2 * LINES), (cuuint32_t)(L / 2), 1, 1};
-            const cuuint64_t sx[3] = {L * 16, (cuuint64_t)in_dist * 16, (cuuint64_t)in_dist * 16 * (cuuint64_t)(ng * UNIT)};
-            const cuuint64_t so[3] = {L * 16, (cuuint64_t)out_dist * 16, (cuuint64_t)out_dist * 16 * (cuuint64_t)(ng * UNIT)};
-            if ((rc = map4(enc, in + g0 * UNIT * in_dist, dims, sx, box, &m_x)) != GD_OK) break;
-            if ((rc = map4(enc, out + g0 * UNIT * out_dist, dims, so, box, &m_out)) != GD_OK) break;
+            const cuuint64_t dx[4] = {2 * Bq, A, nt, 1}, dout[4] = {2 * A, Bq, nt, 1};
+            const cuuint32_t bx[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)(A / 2), 1, 1}, bo[4] = {(cuuint32_t)(2 * LNB), (cuuint32_t)(Bq / 2), 1, 1};
+            const cuuint64_t sx[3] = {Bq * 16, (cuuint64_t)in_dist * 16, clamp_stride((cuuint64_t)in_dist * 16 * nt)};
+            const cuuint64_t so[3] = {A * 16, (cuuint64_t)out_dist * 16, clamp_stride((cuuint64_t)out_dist * 16 * nt)};
+            if ((rc = map4(enc, in + g0 * (long long)UNIT * in_dist, dx, sx, bx, &m_x)) != GD_OK) break;
+            if ((rc = map4(enc, out + g0 * (long long)UNIT * out_dist, dout, so, bo, &m_out)) != GD_OK) break;
         } else {
-            const cuuint64_t dims[4] = {(cuuint64_t)(2 * ng * UNIT), L, L, 1};
-            const cuuint32_t box[4] = {(cuuint32_t)(2 * LINES), 1, (cuuint32_t)(L / 2), 1};
-            const cuuint64_t str[3] = {(cuuint64_t)count * 16, (cuuint64_t)count * 16 * L, (cuuint64_t)count * 16 * L * L};
-            if ((rc = map4(enc, in + g0 * UNIT, dims, str, box, &m_x)) != GD_OK) break;
-            if ((rc = map4(enc, out + g0 * UNIT, dims, str, box, &m_out)) != GD_OK) break;
+            const cuuint64_t pi_ = (cuuint64_t)in_dist * 16, po = (cuuint64_t)out_dist * 16;
+            const cuuint64_t dx[4] = {2 * nt, Bq, A, 1}, dout[4] = {2 * nt, A, Bq, 1};
+            const cuuint32_t bx[4] = {(cuuint32_t)(2 * LNA), 1, (cuuint32_t)(A / 2), 1}, bo[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)SH::RA, (cuuint32_t)(Bq / 2), 1};
+            const cuuint64_t sx[3] = {pi_, pi_ * Bq, clamp_stride(pi_ * N)};
+            const cuuint64_t so[3] = {po, po * A, clamp_stride(po * N)};
+            if ((rc = map4(enc, in + g0 * (long long)UNIT, dx, sx, bx, &m_x)) != GD_OK) break;
+            if ((rc = map4(enc, out + g0 * (long long)UNIT, dout, so, bo, &m_out)) != GD_OK) break;
         }
         f.batch = (int)ng; f.delay = D; f.nslots = S; f.scratch = scratch;
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.scale = scale;
-        f.out = mode == T14_ROWS ? out + g0 * UNIT * out_dist : out + g0 * UNIT;
-        f.out_dist = mode == T14_ROWS ? out_dist : count;
-        f.opt = d.tma_opt >> 4;
         f.prof = nullptr;
         if (d.tma_prof) {
             long long* pr;
@@ -162,9 +164,14 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(counters)"); break; }
         const long long nitems = 2 * ng * 256;
         const int grid = (int)(nitems < d.num_sms ? nitems : d.num_sms);
-        if (f.prof && !inv) e = mode == T14_ROWS ? launch14<LEN, T14_ROWS, false, true>(grid, m_x, m_int, m_out, f, st) : launch14<LEN, T14_COLS, false, true>(grid, m_x, m_int, m_out, f, st);
-        else if (mode == T14_ROWS) e = inv ? launch14<LEN, T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LEN, T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
-        else e = inv ? launch14<LEN, T14_COLS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LEN, T14_COLS, false>(grid, m_x, m_int, m_out, f, st);
+        if constexpr (LB <= 256) {
+            if (f.prof && !inv && LA == LB) e = mode == T14_ROWS ? launch14<LA, LB, T14_ROWS, false, LA == LB>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, LA == LB>(grid, m_x, m_int, m_out, f, st);
+            else if (mode == T14_ROWS) e = inv ? launch14<LA, LB, T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
+            else e = inv ? launch14<LA, LB, T14_COLS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false>(grid, m_x, m_int, m_out, f, st);
+        } else {
+            if (mode != T14_ROWS) { rc = invalid14("fused kernel: columns need LB <= 256"); break; }
+            e = inv ? launch14<LA, LB, T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
+        }
         if (e != cudaSuccess) { rc = cuda_fail(e, "fft_tma14_kernel launch"); break; }
         g_launches++;
     }
@@ -174,5 +181,19 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
     }
     return rc;
 }
+
+// entry points of one size (defined in pass_inst_tma<log2 N>.cu)
+#define GD_TMA2D_ENTRY(LG, LA, LB)                                                                                                      \
+    bool tma##LG##_rows_applicable(const void* in, long long in_dist, const cpx* out, long long out_dist, long long batch, int ld_conj, \
+                                   int st_conj, double scale) {                                                                         \
+        return tma2d_rows_applicable<LA, LB>(in, in_dist, out, out_dist, batch, ld_conj, st_conj, scale);                               \
+    }                                                                                                                                   \
+    bool tma##LG##_cols_applicable(const cpx* src, const cpx* dst, long long len, long long ncols, long long pitch) {                   \
+        return tma2d_cols_applicable<LA, LB>(src, dst, len, ncols, pitch);                                                              \
+    }                                                                                                                                   \
+    Status fft_tma_2p##LG(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, \
+                          double scale, cudaStream_t st) {                                                                              \
+        return fft_tma_2d<LA, LB>(d, mode, in, in_dist, out, out_dist, count, inv, scale, st);                                          \
+    }
 
 }  // namespace gd

@@ -346,36 +346,64 @@ def test_fft2_fused_2p14_lines(gd, rows, cols):  # the fused 2^14 kernel (fft_tm
     finally:
         capi.check(L.gd_set_option(b"tma14", 1))
     assert rel_l2(o2, out) <= 1e-14
-    capi.check(L.gd_set_option(b"tma_opt", 16))  # experiment path: pass-2 output stored from registers; same bits
-    try:
-        o3, b3 = np.empty_like(x), np.empty_like(x)
-        capi.check(L.gd_fft2_c2c(x.ctypes.data, o3.ctypes.data, rows, cols, 1))
-        capi.check(L.gd_fft2_c2c(o3.ctypes.data, b3.ctypes.data, rows, cols, -1))
-    finally:
-        capi.check(L.gd_set_option(b"tma_opt", 0))
-    assert np.array_equal(o3, out) and np.array_equal(b3, back)
+
+
+@pytest.mark.parametrize("lg", [13, 14, 15, 16, 17, 18])
+def test_fused_family_rows_and_columns(gd, lg):
+    """The TMA-fed fused four-step (fft_tma14.cuh) for every size of its family, N = LA x LB = 2^13 .. 2^18: batched contiguous
+    transforms and the columns of an N-row matrix, forward and inverse, with a batch / column count that is not a multiple
+    of a phase (the remainder goes through the two-launch path); sampled lines against the oracle, everything against the
+    two-launch schedule."""
+    _, capi, L = gd
+    import torch
+    n = 1 << lg
+    unit = (1 << 20) // n
+    nb = 2 * unit + 3                                         # two phases + a remainder
+    x = torch.empty(nb * n * 2, dtype=torch.float64, device="cuda")
+    capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), nb * n * 2, 30 + lg, 0, None))
+    capi.check(L.gd_stream_sync(None))
+    xh = x.cpu().numpy().view(np.complex128)
+    outs = {}
+    for fused in (1, 0):
+        capi.check(L.gd_set_option(b"tma14", fused)); capi.check(L.gd_set_option(b"tma16", fused))
+        try:
+            y, z, yc, zc = (torch.empty_like(x) for _ in range(4))
+            l0 = L.gd_kernel_launches()
+            capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, nb, 1, None))
+            capi.check(L.gd_fft_batch_c2c_dev(y.data_ptr(), z.data_ptr(), n, nb, -1, None))
+            nl_rows = L.gd_kernel_launches() - l0
+            ok_cols = lg <= 17
+            if ok_cols:                                       # the same memory as an n x nb matrix: every column is a transform
+                capi.check(L.gd_fft_strided_c2c_dev(x.data_ptr(), yc.data_ptr(), 1, n, nb, 1, None))
+                capi.check(L.gd_fft_strided_c2c_dev(yc.data_ptr(), zc.data_ptr(), 1, n, nb, -1, None))
+            capi.check(L.gd_stream_sync(None))
+            outs[fused] = (y.cpu().numpy().view(np.complex128), z.cpu().numpy().view(np.complex128),
+                           yc.cpu().numpy().view(np.complex128) if ok_cols else None, zc.cpu().numpy().view(np.complex128) if ok_cols else None, nl_rows)
+        finally:
+            capi.check(L.gd_set_option(b"tma14", 1)); capi.check(L.gd_set_option(b"tma16", 1))
+    y, z, yc, zc, nl_fused = outs[1]
+    y0, z0, yc0, zc0, nl_plain = outs[0]
+    assert nl_fused < nl_plain                                # one persistent launch per direction (+ the remainder) instead of chunks
+    for r in (0, 1, unit - 1, unit, 2 * unit - 1, 2 * unit, nb - 1):
+        assert rel_l2(y.reshape(nb, n)[r], oracle.fft(np.ascontiguousarray(xh.reshape(nb, n)[r]))) <= TOL, ("row", r)
+    assert rel_l2(z, xh) <= TOL
+    assert rel_l2(y, y0) <= 1e-14 and rel_l2(z, z0) <= 1e-14
+    if yc is not None:
+        for c in (0, unit - 1, unit, 2 * unit - 1, 2 * unit, nb - 1):
+            assert rel_l2(yc.reshape(n, nb)[:, c], oracle.fft(np.ascontiguousarray(xh.reshape(n, nb)[:, c]))) <= TOL, ("column", c)
+        assert rel_l2(zc, xh) <= TOL
+        assert rel_l2(yc, yc0) <= 1e-14 and rel_l2(zc, zc0) <= 1e-14
 
 
 @pytest.mark.parametrize("rows,cols", [(65536, 32), (32, 65536), (65536, 80), (48, 65536)])
-def test_fft2_fused_2p16_lines(gd, rows, cols):  # the same kernel with 256-point sub-lines: columns of a 2^16-row matrix, batched 2^16 rows
+def test_fft2_fused_2p16_lines(gd, rows, cols):  # 256 x 256 sub-lines: columns of a 2^16-row matrix, batched 2^16 rows (host-pointer API)
     _, capi, L = gd
     x = oracle.splitmix_complex(rows * cols, 4).reshape(rows, cols)
     out, back = np.empty_like(x), np.empty_like(x)
-    l0 = L.gd_kernel_launches()
     capi.check(L.gd_fft2_c2c(x.ctypes.data, out.ctypes.data, rows, cols, 1))
-    fused_launches = L.gd_kernel_launches() - l0
     assert rel_l2(out, oracle.fft2(x)) <= TOL
     capi.check(L.gd_fft2_c2c(out.ctypes.data, back.ctypes.data, rows, cols, -1))
     assert rel_l2(back, x) <= TOL
-    capi.check(L.gd_set_option(b"tma16", 0))     # and the two-launch schedule gives the same result with more launches
-    try:
-        o2 = np.empty_like(x)
-        l0 = L.gd_kernel_launches()
-        capi.check(L.gd_fft2_c2c(x.ctypes.data, o2.ctypes.data, rows, cols, 1))
-        assert L.gd_kernel_launches() - l0 > fused_launches
-    finally:
-        capi.check(L.gd_set_option(b"tma16", 1))
-    assert rel_l2(o2, out) <= 1e-14
 
 
 def test_tma16_fused_stress(gd):                  # race hunt for the 256 x 256 variant, both modes (Parseval per line)
