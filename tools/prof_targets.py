@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """One short invocation of every hot kernel, for `ncu --set full` (profiles/): the fused 2^20 kernel (128 transforms), the
-fused 2^14 kernel in both modes, the bulk-fed Pwelch kernel (2^28 samples), the 32-point-per-thread pass kernel, the
+fused 2^14 kernel in both modes and the 2^15 / 2^16 / 2^18 members of its family, the bulk-fed Pwelch kernel (2^28 samples), the 32-point-per-thread pass kernel, the
 GENERIC Bluestein passes (N = 1,000,003), an FFT2 strided axis of 4096-point lines, and both peer-memory exchange
 kernels (world = 1: the stores go to this GPU's own buffer). Single process, single GPU."""
 import ctypes as C, os, sys
@@ -22,6 +22,12 @@ del x, y
 m, o = dev(16384 * 2048), dev(16384 * 2048); fill(m, 4); sync()
 capi.check(L.gd_fft_strided_c2c_dev(m.data_ptr(), o.data_ptr(), 1, 16384, 2048, 1, None)); sync()
 capi.check(L.gd_fft_batch_c2c_dev(m.data_ptr(), o.data_ptr(), 16384, 2048, 1, None)); sync()
+# 3b. the other sizes of the fused family: 2^16 = 256 x 256 (columns of a 65536 x 512 matrix, rows of 512 x 65536), 2^15 = 256 x 128
+#     and 2^18 = 512 x 512 as batched rows (the same 2^25 points each)
+capi.check(L.gd_fft_strided_c2c_dev(m.data_ptr(), o.data_ptr(), 1, 65536, 512, 1, None)); sync()
+capi.check(L.gd_fft_batch_c2c_dev(m.data_ptr(), o.data_ptr(), 65536, 512, 1, None)); sync()
+capi.check(L.gd_fft_batch_c2c_dev(m.data_ptr(), o.data_ptr(), 32768, 1024, 1, None)); sync()
+capi.check(L.gd_fft_batch_c2c_dev(m.data_ptr(), o.data_ptr(), 262144, 128, 1, None)); sync()
 # 4. an FFT2 axis of 4096-point strided lines (single pass kernel, column mode)
 capi.check(L.gd_fft_strided_c2c_dev(m.data_ptr(), o.data_ptr(), 1, 4096, 8192, 1, None)); sync()
 del m, o

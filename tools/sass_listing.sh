@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 lib=go-dsp_b200/lib/libgodsp_b200.so
 mkdir -p profiles
 cuobjdump -sass $lib > /tmp/all.sass
-for k in fft_tma14_kernelILi0ELb0 fft_tma14_kernelILi1ELb0 pwelch_bulk_kernel; do
+for k in fft_tma14_kernelILi128ELi128ELi0ELb0ELb0 fft_tma14_kernelILi128ELi128ELi1ELb0ELb0 fft_tma14_kernelILi256ELi256ELi0ELb0ELb0 fft_tma14_kernelILi256ELi256ELi1ELb0ELb0 fft_tma14_kernelILi256ELi128ELi0ELb0ELb0 pwelch_bulk_kernel; do
   awk -v pat="$k" '/Function : /{f=index($0,pat)>0} f' /tmp/all.sass | gzip -9 > profiles/${tag}_sass_${k}.txt.gz
 done
 awk '/Function : /{f=index($0,"fft_tma_fused_kernelILb0ELb0")>0} f' /tmp/all.sass > profiles/${tag}_sass_fft_tma_fused_kernel_forward.txt
