@@ -44,14 +44,14 @@ static bool tma2d_rows_applicable(const void* in, long long in_dist, const cpx* 
     using SH = T14Shape<LA, LB>;
     const long long N = SH::N;
     const bool fwd = !ld_conj && !st_conj && scale == 1.0, inv = ld_conj && st_conj;
-    return (fwd || inv) && batch >= 2 * SH::UNIT && batch % SH::UNIT == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && in_dist >= N &&
+    return (fwd || inv) && batch >= SH::UNIT && batch % SH::UNIT == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && in_dist >= N &&
            out_dist >= N && in_dist < (1LL << 35) && out_dist < (1LL << 35);
 }
 // columns [0, ncols) of a row-major matrix with N rows and row pitch `pitch`
 template <int LA, int LB>
 static bool tma2d_cols_applicable(const cpx* src, const cpx* dst, long long len, long long ncols, long long pitch) {
     using SH = T14Shape<LA, LB>;
-    return LB <= 256 && len == (long long)SH::N && ncols >= 2 * SH::UNIT && ncols % SH::UNIT == 0 && pitch >= ncols && pitch < (1LL << 30) &&
+    return LB <= 256 && len == (long long)SH::N && ncols >= SH::UNIT && ncols % SH::UNIT == 0 && pitch >= ncols && pitch < (1LL << 30) &&
            ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
 }
 

@@ -174,10 +174,9 @@ def test_above_2p24_single_gpu(gd):              # the reference has no length l
     X = godsp.fft.FFT(x)
     assert rel_l2(X, oracle.fft(x)) <= TOL
     assert rel_l2(godsp.fft.IFFT(X), x) <= TOL
-    # a Bluestein length whose padded size exceeds 2^24 is refused loudly (documented limit), never computed on the CPU
-    y = np.zeros(9000001, np.complex128)
-    with pytest.raises(godsp.GoPanic, match="2\\^24"):
-        godsp.fft.FFT(y)
+    # a Bluestein length whose padded size exceeds 2^30 is refused loudly (documented limit), never computed on the CPU
+    assert L.gd_plan_warm((1 << 29) + 1) < 0
+    assert "2^30" in L.gd_last_error().decode()
 
 
 def test_bluestein_padding_lengths(gd):
@@ -348,8 +347,9 @@ def test_fft2_fused_2p14_lines(gd, rows, cols):  # the fused 2^14 kernel (fft_tm
     assert rel_l2(o2, out) <= 1e-14
 
 
+@pytest.mark.parametrize("phases", [1, 2])
 @pytest.mark.parametrize("lg", [13, 14, 15, 16, 17, 18])
-def test_fused_family_rows_and_columns(gd, lg):
+def test_fused_family_rows_and_columns(gd, lg, phases):
     """The TMA-fed fused four-step (fft_tma14.cuh) for every size of its family, N = LA x LB = 2^13 .. 2^18: batched contiguous
     transforms and the columns of an N-row matrix, forward and inverse, with a batch / column count that is not a multiple
     of a phase (the remainder goes through the two-launch path); sampled lines against the oracle, everything against the
@@ -358,7 +358,7 @@ def test_fused_family_rows_and_columns(gd, lg):
     import torch
     n = 1 << lg
     unit = (1 << 20) // n
-    nb = 2 * unit + 3                                         # two phases + a remainder
+    nb = phases * unit + 3                                    # whole phases + a remainder
     x = torch.empty(nb * n * 2, dtype=torch.float64, device="cuda")
     capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), nb * n * 2, 30 + lg, 0, None))
     capi.check(L.gd_stream_sync(None))
@@ -376,6 +376,16 @@ def test_fused_family_rows_and_columns(gd, lg):
             if ok_cols:                                       # the same memory as an n x nb matrix: every column is a transform
                 capi.check(L.gd_fft_strided_c2c_dev(x.data_ptr(), yc.data_ptr(), 1, n, nb, 1, None))
                 capi.check(L.gd_fft_strided_c2c_dev(yc.data_ptr(), zc.data_ptr(), 1, n, nb, -1, None))
+            if fused:                                         # in place: pass 2 of a phase starts only after all its pass-1 tiles were read
+                w = x.clone()
+                capi.check(L.gd_fft_batch_c2c_dev(w.data_ptr(), w.data_ptr(), n, nb, 1, None))
+                capi.check(L.gd_stream_sync(None))
+                assert torch.equal(w, y), "in-place rows differ"
+                if ok_cols:
+                    w = x.clone()
+                    capi.check(L.gd_fft_strided_c2c_dev(w.data_ptr(), w.data_ptr(), 1, n, nb, 1, None))
+                    capi.check(L.gd_stream_sync(None))
+                    assert torch.equal(w, yc), "in-place columns differ"
             capi.check(L.gd_stream_sync(None))
             outs[fused] = (y.cpu().numpy().view(np.complex128), z.cpu().numpy().view(np.complex128),
                            yc.cpu().numpy().view(np.complex128) if ok_cols else None, zc.cpu().numpy().view(np.complex128) if ok_cols else None, nl_rows)
@@ -383,13 +393,14 @@ def test_fused_family_rows_and_columns(gd, lg):
             capi.check(L.gd_set_option(b"tma14", 1)); capi.check(L.gd_set_option(b"tma16", 1))
     y, z, yc, zc, nl_fused = outs[1]
     y0, z0, yc0, zc0, nl_plain = outs[0]
-    assert nl_fused < nl_plain                                # one persistent launch per direction (+ the remainder) instead of chunks
-    for r in (0, 1, unit - 1, unit, 2 * unit - 1, 2 * unit, nb - 1):
+    if phases == 2:
+        assert nl_fused < nl_plain                            # one persistent launch per direction (+ the remainder) instead of chunks
+    for r in sorted({0, 1, unit - 1, unit, phases * unit - 1, phases * unit, nb - 1}):
         assert rel_l2(y.reshape(nb, n)[r], oracle.fft(np.ascontiguousarray(xh.reshape(nb, n)[r]))) <= TOL, ("row", r)
     assert rel_l2(z, xh) <= TOL
     assert rel_l2(y, y0) <= 1e-14 and rel_l2(z, z0) <= 1e-14
     if yc is not None:
-        for c in (0, unit - 1, unit, 2 * unit - 1, 2 * unit, nb - 1):
+        for c in sorted({0, unit - 1, unit, phases * unit - 1, phases * unit, nb - 1}):
             assert rel_l2(yc.reshape(n, nb)[:, c], oracle.fft(np.ascontiguousarray(xh.reshape(n, nb)[:, c]))) <= TOL, ("column", c)
         assert rel_l2(zc, xh) <= TOL
         assert rel_l2(yc, yc0) <= 1e-14 and rel_l2(zc, zc0) <= 1e-14
