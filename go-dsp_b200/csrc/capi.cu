@@ -327,6 +327,7 @@ static int set_option_one(Device& d, const char* key, int64_t value) {
     else if (!strcmp(key, "pwelch_bulk")) d.pwelch_bulk = value != 0;
     else if (!strcmp(key, "fanout_min_log2n")) { if (value < 12 || value > 40) return (int)invalid_arg("fanout_min_log2n out of range"); g_fanout_min_log2n.store((int)value); }
     else if (!strcmp(key, "fourstep_pipeline")) d.fourstep_pipeline = value != 0;
+    else if (!strcmp(key, "fourstep_lines_sms")) { if (value < 0 || value > 1024) return (int)invalid_arg("fourstep_lines_sms out of range"); d.fourstep_lines_sms = (int)value; }
     else if (!strcmp(key, "fourstep_exchange_ctas")) d.fourstep_exchange_ctas = (int)value;
     else if (!strcmp(key, "fourstep_pipeline_mb")) { if (value < 1) return (int)invalid_arg("fourstep_pipeline_mb < 1"); d.fourstep_pipeline_mb = (int)value; }
     else if (!strcmp(key, "wide_tiles")) d.wide_tiles = value != 0;
@@ -338,6 +339,7 @@ static int set_option_one(Device& d, const char* key, int64_t value) {
     else if (!strcmp(key, "tma_opt")) d.tma_opt = (int)value;
     else if (!strcmp(key, "tma14")) d.use_tma14 = value != 0;
     else if (!strcmp(key, "tma16")) d.use_tma16 = value != 0;
+    else if (!strcmp(key, "tma_grid_cap")) { if (value < 0 || value > 1024) return (int)invalid_arg("tma_grid_cap out of range"); d.tma_grid_cap = (int)value; }
     else if (!strcmp(key, "tma_prof")) d.tma_prof = value != 0;
     else if (!strcmp(key, "tma_delay")) { if (value < 0 || value > 4) return (int)invalid_arg("tma_delay out of range"); d.tma_delay = (int)value; }
     else if (!strcmp(key, "tma_slots")) { if (value < 2 || value > 6) return (int)invalid_arg("tma_slots out of range"); d.tma_slots = (int)value; }

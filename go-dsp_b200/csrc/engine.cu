@@ -681,13 +681,20 @@ Status fourstep_lines_exchange(Device& d, const cpx* slab, cpx* tmp, cpx* const*
     if (st == sx) return invalid("fourstep_lines_exchange: stream clash");
     cudaEventRecord(d.ev_fork, st);
     cudaStreamWaitEvent(sx, d.ev_fork, 0);
-    for (long long c0 = 0; c0 < w; c0 += pb) {
+    // the fused line kernel is persistent with one CTA per SM: while an exchange runs beside it, it leaves some SMs free
+    const int saved_cap = d.tma_grid_cap;
+    if (d.fourstep_lines_sms > 0) d.tma_grid_cap = d.fourstep_lines_sms;
+    Status rc = GD_OK;
+    for (long long c0 = 0; c0 < w && rc == GD_OK; c0 += pb) {
         const long long nc = w - c0 < pb ? w - c0 : pb;
-        GD_TRY(fft_axis(d, slab, tmp, 1, n1, w, +1, st, c0, nc));
-        GD_CUDA(cudaEventRecord(d.ev_pipe, st));
-        GD_CUDA(cudaStreamWaitEvent(sx, d.ev_pipe, 0));
-        GD_TRY(fourstep_exchange(tmp, peer_recv, n1, w, rank, world, log2n, sx, c0, nc, d.fourstep_exchange_ctas));
+        rc = fft_axis(d, slab, tmp, 1, n1, w, +1, st, c0, nc);
+        if (rc != GD_OK) break;
+        cudaEventRecord(d.ev_pipe, st);
+        cudaStreamWaitEvent(sx, d.ev_pipe, 0);
+        rc = fourstep_exchange(tmp, peer_recv, n1, w, rank, world, log2n, sx, c0, nc, d.fourstep_exchange_ctas);
     }
+    d.tma_grid_cap = saved_cap;
+    GD_TRY(rc);
     GD_CUDA(cudaEventRecord(d.ev_pipe, sx));
     GD_CUDA(cudaStreamWaitEvent(st, d.ev_pipe, 0));
     return GD_OK;
@@ -954,7 +961,7 @@ Status convolve_linear(Device& d, const cpx* x, long long nx, const cpx* h, long
 static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, long long len, long long s, int dir, cudaStream_t st,
                        long long col0, long long ncols) {
     const long long nlines = outer * s;
-    const bool sub = ncols >= 0 && !(col0 == 0 && ncols == s);
+    bool sub = ncols >= 0 && !(col0 == 0 && ncols == s);
     if (len == 1) {
         if (src != dst) GD_CUDA(cudaMemcpyAsync(dst, src, (size_t)nlines * sizeof(cpx), cudaMemcpyDeviceToDevice, st));
         return GD_OK;
@@ -973,18 +980,20 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
     }
     if (sub && !(is_pow2(len) && len > 4096 && len <= (1LL << 24) && (double)len * (double)s < 2147483648.0))
         return invalid("fft_axis: a column range needs a power-of-two length in (4096, 2^24]");
-    if (const Tma2dEntry* te = (!sub && p2) ? tma2d_entry(d, ilog2ll(len)) : nullptr) {
+    if (const Tma2dEntry* te = p2 ? tma2d_entry(d, ilog2ll(len)) : nullptr) {
         // columns of a matrix with 2^13 .. 2^17 rows (2^14: fft.FFT2 on 16384 x 16384; 2^16: the line passes of the sharded
         // 2^32-point transform): whole phases of columns in one fused launch, intermediate resident in L2 (fft_tma14.cuh);
         // a remainder of less than one phase of columns goes through the column-range path below
-        const long long main = s - s % te->unit;
-        if (main > 0 && te->cols_ok(src, dst, len, main, s)) {
+        const long long cfirst = sub ? col0 : 0, ctotal = sub ? ncols : s;
+        const long long main = ctotal - ctotal % te->unit;
+        if (main > 0 && te->cols_ok(src + cfirst, dst + cfirst, len, main, s)) {
             for (long long o = 0; o < outer; o++)
-                GD_TRY(te->run(d, 1, src + o * len * s, s, dst + o * len * s, s, main, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
-            if (main == s) return GD_OK;
-            return fft_axis(d, src, dst, outer, len, s, dir, st, main, s - main);
+                GD_TRY(te->run(d, 1, src + o * len * s + cfirst, s, dst + o * len * s + cfirst, s, main, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
+            if (main == ctotal) return GD_OK;
+            col0 = cfirst + main; ncols = ctotal - main;            // the remainder: fewer columns than a phase, two-launch path below
         }
     }
+    sub = ncols >= 0 && !(col0 == 0 && ncols == s);
     if (p2 && len <= (1LL << 24) && fits31) {
         // strided four-step on blocks of cb adjacent columns; the inter-pass block [len][cb] stays in L2
         const int lg = ilog2ll(len), l1 = (lg + 1) / 2, l2 = lg - l1;

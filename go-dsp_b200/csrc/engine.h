@@ -85,6 +85,7 @@ struct Device {
     size_t l2_block_budget = 24ull << 20;       // inter-pass block of one chunk: small enough to stay in L2 between the passes
     bool fourstep_pipeline = false;             // sharded four-step: exchange of a column block behind the lines of the next (measured: no gain)
     int fourstep_pipeline_mb = 256;             // slab bytes per pipeline block
+    int fourstep_lines_sms = 0;                 // pipelined sharded four-step: CTAs of the fused line kernel while an exchange runs beside it (0 = all SMs)
     int fourstep_exchange_ctas = 0;             // cap on the CTAs of a pipelined exchange launch (0 = one per tile)
     bool pwelch_bulk = true;                    // L = 4096 float64: bulk-copy fed kernel (pwelch.cu)
     int chunk_streams = 2;                      // streams the chunks of one call rotate over (1 .. 1 + AUX_STREAMS)
@@ -105,6 +106,7 @@ struct Device {
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)
     bool use_tma14 = true;               // 2^14-point lines (batched rows, columns of a 2^14-row matrix): fused kernel of fft_tma14.cuh
+    int tma_grid_cap = 0;                // fused size family: at most this many CTAs (0 = one per SM); leaves SMs to a concurrent kernel
     bool use_tma16 = true;               // 2^16-point lines: the same kernel with 256-point sub-lines
     int tma_opt = 0;                     // measurement switches of the fused kernel (TmaFusedParams::opt)
     int tma_prof = 0;                    // measurement: cycle counters of the fused kernel (gd_tma_profile_read)

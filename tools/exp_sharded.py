@@ -27,7 +27,7 @@ m = torch.empty(rg * Cc, dtype=torch.complex128, device="cuda")
 res = torch.empty_like(m)
 capi.check(L.gd_fill_splitmix_dev(m.data_ptr(), 2 * rg * Cc, 4, 2 * rank * rg * Cc, st.cuda_stream))
 peers = (D.PeerExchange(rg * Cc, ops), D.PeerExchange(rg * Cc, ops))
-DEFAULTS = {"l2_block_mb": 24, "chunk_streams": 2, "fourstep_pipeline": 0, "fourstep_pipeline_mb": 256, "fourstep_exchange_ctas": 0, "tma14": 1}
+DEFAULTS = {"l2_block_mb": 24, "chunk_streams": 2, "fourstep_pipeline": 0, "fourstep_pipeline_mb": 256, "fourstep_exchange_ctas": 0, "fourstep_lines_sms": 0, "tma14": 1}
 
 def timeit(fn, reps=3):
     for _ in range(2): fn()
