@@ -92,11 +92,16 @@ FP64_INST_PER_POINT_FFT = (2 * (2 * 376 + 240) + 265) / 32.0          # 70.3
 FP64_INST_PER_SAMPLE_PWELCH = 734 / 16.0                              # 45.9 (one 4096-point complex transform per 4096 new samples)
 
 
-def pcie_ceiling(torch, dist, world, barrier, nbytes):
+def pcie_ceiling(torch, dist, world, barrier, nbytes, hin=None, hout=None):
     """What the box's PCIe / host memory gives when every rank copies nbytes up and nbytes down AT THE SAME TIME (pinned
-    memory, two streams, no kernels): the ceiling of the end-to-end numbers at this GPU count."""
+    memory, two streams, no kernels): the ceiling of the end-to-end numbers at this GPU count. hin / hout: addresses of
+    pinned buffers to copy from / to (the e2e run's own NUMA-local gd_pinned_alloc buffers); torch-pinned memory otherwise."""
     try:
-        hp, hq = torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        if hin and hout:
+            hp = torch.frombuffer((C.c_ubyte * nbytes).from_address(hin), dtype=torch.uint8)
+            hq = torch.frombuffer((C.c_ubyte * nbytes).from_address(hout), dtype=torch.uint8)
+        else:
+            hp, hq = torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         dp, dq = torch.empty(nbytes, dtype=torch.uint8, device="cuda"), torch.empty(nbytes, dtype=torch.uint8, device="cuda")
         s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
@@ -118,7 +123,8 @@ def pcie_ceiling(torch, dist, world, barrier, nbytes):
             dt = float(t.item())
         return {"each_way_gbs_per_gpu": nbytes / dt / 1e9, "each_way_gbs_aggregate": world * nbytes / dt / 1e9,
                 "e2e_gs_per_s_at_this_ceiling": world * nbytes / dt / 1e9 / 16.0,
-                "how": "every rank copies %d MiB host->device and device->host concurrently from torch-pinned memory, max over ranks" % (nbytes >> 20)}
+                "how": "every rank copies %d MiB host->device and device->host concurrently from %s, max over ranks"
+                       % (nbytes >> 20, "the e2e run's own pinned buffers (gd_pinned_alloc, NUMA-local)" if hin and hout else "torch-pinned memory")}
     except Exception as ex:
         return {"unavailable": str(ex)[:120]}
 
@@ -480,15 +486,15 @@ def run_ours(args):
             capi.check(L.gd_fft_batch_c2c(hin, hout, n, eb, 1))
 
         ems = timed_host(e2e_step, args.e2e_steps, 1)
-        line["e2e_pcie_ceiling"] = pcie_ceiling(torch, dist, world, barrier, min(nbytes, 1 << 30))
+        hout_keep = np.ctypeslib.as_array((C.c_double * (2 * n)).from_address(hout)).copy()      # the ceiling run overwrites hout
+        line["e2e_pcie_ceiling"] = pcie_ceiling(torch, dist, world, barrier, min(nbytes, 1 << 30), hin, hout)
         line["e2e"] = {"value": eb * n * world / (ems * 1e-3) / 1e9, "unit": "GS/s", "h2d_bytes_per_step": nbytes,
                        "d2h_bytes_per_step": nbytes, "ms_per_step": ems, "batch_per_gpu": eb,
                        "api": "gd_fft_batch_c2c (pinned host in/out; chunked H2D / kernels / D2H overlap on 3 streams)"}
         # spot check: e2e output equals the device-resident output for the same rows
-        hout_np = np.ctypeslib.as_array((C.c_double * (eb * n * 2)).from_address(hout))
         ref = y[: 2 * n].cpu().numpy()
-        line["e2e"]["matches_device_path"] = bool(np.array_equal(hout_np[: 2 * n], ref))
-        del hin_np, hout_np
+        line["e2e"]["matches_device_path"] = bool(np.array_equal(hout_keep, ref))
+        del hin_np
         L.gd_pinned_free(hin)
         L.gd_pinned_free(hout)
         # the same call on PAGEABLE host memory -- what fft.FFT(x) on a plain Go slice hands the library: chunks go through
@@ -536,7 +542,10 @@ def run_ours(args):
             if px is not None:
                 px.close()
 
-    for key in ("pwelch", "fft2", "fft_1d_sharded"):
+        line["fft_sizes"] = run_fft_sizes(args, torch, dist, L, sp, world, rank, timed, hbm_peak)
+        line["gpu_launches"] += line["fft_sizes"].pop("_launches")
+
+    for key in ("pwelch", "fft2", "fft_1d_sharded", "fft_sizes"):
         if key in line and "_parity" in line[key]:
             parity[key] = line[key].pop("_parity")
     parity["max_rel_l2"] = max([v["max_rel_l2"] for v in parity.values()] or [0.0])
@@ -549,6 +558,36 @@ def run_ours(args):
         dist.destroy_process_group()
     if not parity["ok"]:
         raise SystemExit("bench.py: parity check failed: %r" % (parity,))
+
+
+def run_fft_sizes(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
+    """Batched transforms of the other power-of-two sizes with a fused kernel (2^13 .. 2^18, fft_tma14.cuh): 2^28 points per
+    GPU and call, device resident (inputs larger than L2); one row of every size against the oracle."""
+    from godsp import _capi as capi
+    import oracle
+    total = 1 << 28
+    x = torch.empty(total * 2, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), total * 2, 11, (rank * total) * 2, sp))
+    torch.cuda.synchronize()
+    rows, worst, launches = {}, 0.0, 0
+    for lg in range(13, 19):
+        n = 1 << lg
+        b = total // n
+        ms, nl, _ = timed(lambda: capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, b, 1, sp)), 3, 3)
+        launches += nl
+        r = b - 1                                            # the last transform of the batch against the oracle
+        xin = x.view(b, 2 * n)[r].cpu().numpy().view(np.complex128)
+        got = y.view(b, 2 * n)[r].cpu().numpy().view(np.complex128)
+        err = rel_l2(got, oracle.fft(np.ascontiguousarray(xin)))
+        worst = max(worst, err)
+        rows["2^%d" % lg] = {"gs_per_gpu": n * b / (ms * 1e-3) / 1e9, "ms": ms, "hbm_frac": 32.0 * n * b / (ms * 1e-3) / 1e9 / hbm_peak}
+    del x, y
+    torch.cuda.empty_cache()
+    return {"metric": "FFT GS/s per GPU (complex128, batched, 2^28 points per call) by transform size", "sizes": rows,
+            "kernel": "gd::fft_tma14_kernel<LA, LB, ROWS> (both four-step passes in one persistent TMA-fed launch, N = LA x LB)",
+            "_parity": {"max_rel_l2": allmax(torch, dist, world, worst), "vs": "oracle.fft on the last transform of every batch, every rank"},
+            "_launches": int(launches)}
 
 
 def run_fft2(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
