@@ -266,6 +266,37 @@ __global__ void pwelch_fold_kernel(const double* __restrict__ partial, long long
     raw[j] = 0.5 * (s0 + s1);
 }
 
+// power-of-two fftlen above 4096: two real segments ride in one complex transform here as well (see the top of the file).
+// z[u][n] = win[n] * (a[n] + i b[n]), a = segment seg0 + 2 (u0 + u), b = the next one (0 past the last segment), zero-padded
+__global__ void pwelch_pack_pairs_kernel(const void* __restrict__ x, int fmt, long long nfft, long long stride, long long seg0,
+                                         long long nseg, long long u0, long long npairs, long long fftlen,
+                                         const double* __restrict__ win, cpx* __restrict__ buf) {
+    const long long tot = npairs * fftlen, step = (long long)gridDim.x * blockDim.x;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot; t += step) {
+        const long long u = t / fftlen, n = t - u * fftlen, sa = 2 * (u0 + u);
+        double a = 0.0, b = 0.0;
+        if (n < nfft) {
+            const double w = __ldg(win + n);
+            a = w * load_sample_rt(x, (seg0 + sa) * stride + n, fmt);
+            if (sa + 1 < nseg) b = w * load_sample_rt(x, (seg0 + sa + 1) * stride + n, fmt);
+        }
+        buf[t] = make_double2(a, b);
+    }
+}
+// partial[g][k] (+)= sum over the pairs u = g, g + G, ... of this chunk (ascending) of |Z_u[k]|^2: a fixed summation order
+__global__ void pwelch_accum_pairs_kernel(const cpx* __restrict__ buf, long long npairs, long long fftlen, int first,
+                                          double* __restrict__ partial) {
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= fftlen) return;
+    const long long g = blockIdx.y, G = gridDim.y;
+    double s = first ? 0.0 : partial[g * fftlen + k];
+    for (long long u = g; u < npairs; u += G) {
+        const cpx v = buf[u * fftlen + k];
+        s = fma(v.x, v.x, fma(v.y, v.y, s));
+    }
+    partial[g * fftlen + k] = s;
+}
+
 // general path (any fftlen): dense windowed, zero-padded complex segments
 __global__ void pwelch_gather_kernel(const void* __restrict__ x, int fmt, long long nfft, long long stride, long long seg0,
                                      long long nseg, long long fftlen, const double* __restrict__ win, cpx* __restrict__ buf) {
@@ -396,6 +427,39 @@ Status pwelch_partial(Device& d, const void* x, int fmt, long long nfft, long lo
             case 2048: return launch_fused<11>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
             case 4096: return launch_fused<12>(d, x, fmt, nfft, stride, lp, seg0, nseg, win, raw, st);
         }
+    }
+    if (p2 && fftlen > 4096) {
+        // pairs of segments packed into complex transforms -> batched power-of-two transforms (the fused size family up to
+        // 2^18 points) -> per-bin sums over groups of pairs in a fixed order -> the fold of the fused path
+        const long long npairs = (nseg + 1) / 2;
+        long long cp = (long long)((1ull << 30) / ((size_t)fftlen * sizeof(cpx)));          // pairs per chunk: 1 GiB of spectra
+        if (cp < 1) cp = 1;
+        if (cp > npairs) cp = npairs;
+        const long long unit = fftlen <= (1LL << 18) ? (1LL << 20) / fftlen : 1;             // whole phases of the fused kernel
+        if (cp > unit) cp -= cp % unit;
+        long long G = (1LL << 23) / fftlen;                                                 // groups: partial sums of 64 MiB at most
+        if (G > 128) G = 128;
+        if (G > cp) G = cp;
+        if (G < 1) G = 1;
+        cpx* buf;
+        double* partial;
+        GD_TRY(d.ensure_scratch(SCR_PWELCH, (size_t)cp * fftlen * sizeof(cpx), (void**)&buf));
+        GD_TRY(d.ensure_scratch(SCR_AUX, (size_t)G * fftlen * sizeof(double), (void**)&partial));
+        for (long long u0 = 0; u0 < npairs; u0 += cp) {
+            const long long np_ = npairs - u0 < cp ? npairs - u0 : cp;
+            long long pg = (np_ * fftlen + 255) / 256;
+            if (pg > (long long)d.num_sms * 32) pg = (long long)d.num_sms * 32;
+            pwelch_pack_pairs_kernel<<<(unsigned)pg, 256, 0, st>>>(x, fmt, nfft, stride, seg0, nseg, u0, np_, fftlen, win, buf);
+            GD_CUDA(cudaGetLastError());
+            GD_TRY(fft1d(d, buf, fftlen, buf, fftlen, fftlen, np_, false, +1, st));
+            pwelch_accum_pairs_kernel<<<dim3((unsigned)((fftlen + 255) / 256), (unsigned)G, 1), 256, 0, st>>>(buf, np_, fftlen, u0 == 0 ? 1 : 0, partial);
+            GD_CUDA(cudaGetLastError());
+            g_launches += 2;
+        }
+        pwelch_fold_kernel<<<(unsigned)((lp + 127) / 128), 128, 0, st>>>(partial, G, (int)fftlen, lp, raw);
+        g_launches++;
+        GD_CUDA(cudaGetLastError());
+        return GD_OK;
     }
     // general path: dense windowed segments -> batched transform (any length) -> per-bin sums
     long long chunk = (long long)((64ull << 20) / ((size_t)fftlen * sizeof(cpx)));

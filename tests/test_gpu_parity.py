@@ -509,6 +509,22 @@ def test_pwelch_custom_window_closure(gd):       # PwelchOptions.Window is an ar
     assert rel_l2(p, pw) <= TOL and np.array_equal(f, fw)
 
 
+@pytest.mark.parametrize("case", [(1 << 21, 8192, 4096, 0, "Hann"), ((1 << 21) + 5000, 8192, 1000, 0, "Hamming"),
+                                  (1 << 22, 16384, 8192, 32768, "Hann"), (3 * (1 << 20), 65536, 0, 0, "Rectangular"),
+                                  (1 << 22, 262144, 131072, 0, "Hann"), (1 << 22, 1 << 20, 1 << 19, 0, "Hann"),
+                                  (1 << 20, 6000, 3000, 8192, "Hann")])
+def test_pwelch_large_nfft(gd, case):            # power-of-two transform lengths above 4096: pairs of segments per complex transform
+    """NFFT / Pad beyond the fused kernel's 4096 points: segment pairs packed into complex transforms, batched through the fused
+    size family (2^13 .. 2^18) or the chunked passes, per-bin sums in a fixed order; even and odd segment counts."""
+    godsp = gd[0]
+    nx, nfft, nov, pad, wname = case
+    x = oracle.fill_splitmix(nx, 5)
+    p, f = godsp.spectral.Pwelch(x, 2.0, godsp.spectral.PwelchOptions(NFFT=nfft, Window=getattr(godsp.window, wname), Pad=pad, Noverlap=nov))
+    pw, fw = oracle.pwelch(x, 2.0, nfft=nfft, pad=pad, noverlap=nov, window_fn=wname.lower(), threads=8)
+    assert len(p) == len(pw) and np.array_equal(f.view(np.uint64), fw.view(np.uint64))
+    assert rel_l2(p, pw) <= TOL
+
+
 def test_pwelch_config4_sample(gd):              # C4 shape (NFFT 4096, 50% overlap, Hann) on 2^24 samples vs the oracle
     godsp = gd[0]
     x = oracle.fill_splitmix(1 << 24, 5)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Pwelch kernel timing through the C ABI (device-resident). usage: exp_pwelch.py [--log2 30] "opt=val,..." ..."""
+"""Pwelch kernel timing through the C ABI (device-resident). usage: exp_pwelch.py [--log2 30] [--nfft 4096] "opt=val,..." ..."""
 import json, os, sys
 import numpy as np
 import torch
@@ -8,10 +8,13 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "go-dsp_b200"))
 from godsp import _capi as capi
 from godsp import window as gw
 args = sys.argv[1:]; lg = 30
-if args and args[0] == "--log2":
-    lg = int(args[1]); args = args[2:]
+nfft = 4096
+while args and args[0] in ("--log2", "--nfft"):
+    if args[0] == "--log2": lg = int(args[1])
+    else: nfft = int(args[1])
+    args = args[2:]
 L = capi.lib(); capi.check(L.gd_use_device(0))
-ns, nfft, nov = 1 << lg, 4096, 2048
+ns, nov = 1 << lg, nfft // 2
 stride = nfft - nov
 nsegs = (ns - nfft) // stride + 1
 lp = nfft // 2 + 1
@@ -41,5 +44,5 @@ for combo in (args or [""]):
     r = raw.cpu().numpy().copy()
     if ref is None:
         ref = r
-    print(json.dumps({"opts": combo, "log2_samples": lg, "msamples_per_s_best": ns / min(ts) / 1e3, "ms_best": min(ts),
+    print(json.dumps({"opts": combo, "nfft": nfft, "log2_samples": lg, "msamples_per_s_best": ns / min(ts) / 1e3, "ms_best": min(ts),
                       "rel_diff_vs_first": float(np.linalg.norm(r - ref) / np.linalg.norm(ref))}), flush=True)
