@@ -26,12 +26,12 @@ int pass32_tile_lines(int variant);
                                    int st_conj, double scale);                                                                           \
     bool tma##LG##_cols_applicable(const cpx* src, const cpx* dst, long long len, long long ncols, long long pitch);                     \
     Status fft_tma_2p##LG(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, \
-                          double scale, cudaStream_t st);
+                          double scale, cudaStream_t st, int tw2_log2m, long long tw2_col0);
 GD_TMA2D_DECL(13) GD_TMA2D_DECL(14) GD_TMA2D_DECL(15) GD_TMA2D_DECL(16) GD_TMA2D_DECL(17) GD_TMA2D_DECL(18)
 struct Tma2dEntry {
     bool (*rows_ok)(const void*, long long, const cpx*, long long, long long, int, int, double);
     bool (*cols_ok)(const cpx*, const cpx*, long long, long long, long long);
-    Status (*run)(Device&, int, const cpx*, long long, cpx*, long long, long long, bool, double, cudaStream_t);
+    Status (*run)(Device&, int, const cpx*, long long, cpx*, long long, long long, bool, double, cudaStream_t, int, long long);
     int unit;                                            // transforms / columns per phase: 2^20 / N
 };
 static const Tma2dEntry* tma2d_entry(const Device& d, int log2n) {
@@ -198,6 +198,14 @@ Status Device::twiddles(int log2m, TwiddleTable* out) {
     return GD_OK;
 }
 
+// keeps the persisting L2 set-aside carved for its lifetime: handing it back (cudaCtxResetPersistingL2Cache + limit 0) and carving
+// it again between the launches of a chunk loop costs tens of microseconds of host time each way
+struct L2Hold {
+    Device& d;
+    explicit L2Hold(Device& dv) : d(dv) { d.l2_hold++; }
+    ~L2Hold() { d.l2_hold--; }
+};
+
 // ------------------------------------------------------------------ pass dispatch
 static Status launch_pass(Device& d, int log2l, const PassParams& p, cudaStream_t st) {
     bool generic = (p.ld_flags & (LD_REAL | LD_PAD | LD_MULAUX | LD_REVERSE)) ||
@@ -250,7 +258,7 @@ struct ForkJoin {
         }
         set(base, bytes < d.l2_window_max ? bytes : d.l2_window_max, (double)want);
         window = true;
-        d.l2_hold = true;                    // launch_pass must not hand the set-aside back between the chunks
+        d.l2_hold++;                         // launch_pass must not hand the set-aside back between the chunks
     }
     void set(void* base, size_t bytes, double carved) {
         cudaStreamAttrValue attr;
@@ -267,7 +275,7 @@ struct ForkJoin {
         for (int i = 0; i + 1 < ways; i++) cudaStreamSetAttribute(d.stream_aux[i], cudaStreamAttributeAccessPolicyWindow, &attr);
     }
     ~ForkJoin() {
-        if (window) { set(nullptr, 0, 0.0); d.l2_hold = false; d.l2_dirty = true; }
+        if (window) { set(nullptr, 0, 0.0); d.l2_hold--; d.l2_dirty = true; }
         for (int i = 0; i + 1 < ways; i++) { cudaEventRecord(d.ev_join[i], d.stream_aux[i]); cudaStreamWaitEvent(st, d.ev_join[i], 0); }
     }
 };
@@ -277,9 +285,13 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
                        long long col0 = 0, long long ncols = -1);
 Status transpose_batched(const cpx* in, cpx* out, long long batch, long long rows, long long cols, cudaStream_t st);
 
-// N = 2^25 .. 2^34 on one GPU: an outer four-step over the building blocks below 2^24 (the reference has no length limit,
-// fft/fft.go:72-87). x as a row-major [N1][N2] matrix: (1) every column, length N1, strided lines; (2) w_N^(n2 k1), phases
-// by sincospi of exactly reduced exponents; (3) every row, length N2; (4) X[k1 + N1 k2] = result[k1][k2]: one transpose.
+// Large single transforms (2^22 .. 2^34 points; the reference has no length limit, fft/fft.go:72-87) as an outer four-step over
+// the fused size family. x is a row-major [N1][N2] matrix.
+//  two sweeps (N2 <= 4096, N1 = 2^13 .. 2^17): (1) every column through the fused kernel in column mode, whose stores carry
+//      w_N^(n2 k1) (TW2 in fft_tma14.cuh); (2) every row (length N2, contiguous) through one pass kernel with the transposed store
+//      X[k1 + N1 k2]: tiles of T adjacent rows write T x 16 contiguous bytes per k2.
+//  three sweeps (beyond): (1) as above, (2) one transpose to [N2][N1], (3) columns of length N2 in place: out[k2][k1] = X[k1 + N1 k2].
+//  four sweeps (huge_sweeps = 4, the first formulation: columns, twiddle kernel, rows, transpose) stay as the cross-check.
 // Forward and inverse (every sub-step inverted, conjugate twiddle) only; needs a second N-element buffer.
 static Status fft_pow2_huge(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, int log2n, long long batch,
                             const FusedOps& ops, cudaStream_t st) {
@@ -288,13 +300,42 @@ static Status fft_pow2_huge(Device& d, const void* in, long long in_dist, cpx* o
     if (!fwd && !inv) return invalid("transforms above 2^24 points support plain forward / inverse only (no Bluestein above a padded length of 2^24)");
     if (log2n > 34) return invalid("fft_pow2: N > 2^34");
     const int dir = inv ? -1 : +1;
-    const int l1 = (log2n + 1) / 2, l2 = log2n - l1;
-    const long long N = 1LL << log2n, N1 = 1LL << l1, N2 = 1LL << l2;
+    const long long N = 1LL << log2n;
     cpx* tmp;
     GD_TRY(d.ensure_scratch(SCR_HUGE, (size_t)N * sizeof(cpx), (void**)&tmp));
+    // the split: N1 through the fused family in column mode (2^13 .. 2^17 rows), N2 = N / N1
+    int l1 = d.huge_l1 ? d.huge_l1 : (log2n <= 24 ? 16 : log2n <= 29 ? 17 : (log2n + 1) / 2);
+    if (l1 > log2n - 4) l1 = log2n - 4;
+    int l2 = log2n - l1;
+    const Tma2dEntry* te = (d.huge_sweeps != 4 && l1 >= 13 && l1 <= 17) ? tma2d_entry(d, l1) : nullptr;
+    const bool three = te && (l2 > 12 || d.huge_sweeps == 3);
+    if (te && !three && l2 > 12) te = nullptr;
+    if (!te) { l1 = (log2n + 1) / 2; l2 = log2n - l1; }
+    const long long N1 = 1LL << l1, N2 = 1LL << l2;
+    // the fused kernel's persisting L2 set-aside stays carved across the sweeps and the transforms of the batch (handing it back and
+    // carving it again around every pass kernel costs more host time than a 2^21-point transform takes)
+    L2Hold hold(d);
     for (long long b = 0; b < batch; b++) {
         const cpx* src = (const cpx*)in + b * in_dist;
         cpx* dst = out + b * out_dist;
+        if (te && te->cols_ok(src, tmp, N1, N2, N2)) {
+            cpx* mid = three ? dst : tmp;                                        // three sweeps: columns -> dst, transpose -> tmp, columns -> dst
+            GD_TRY(te->run(d, 1, src, N2, mid, N2, N2, inv, inv ? 1.0 / (double)N1 : 1.0, st, log2n, 0));   // (1) columns n2, twiddle on store
+            if (three) {
+                GD_TRY(transpose_batched(mid, tmp, 1, N1, N2, st));              // (2) [N1][N2] -> [N2][N1]
+                GD_TRY(fft_axis(d, tmp, dst, 1, N2, N1, dir, st));               // (3) lines over n2 at stride N1
+                continue;
+            }
+            PassParams r = base_params(d, l2);                                   // (2) rows k1 of tmp -> X[k1 + N1 k2]
+            r.in = tmp; r.out = dst;
+            r.nlines = N1; r.inner = N1;
+            r.in_qs = N; r.in_is = N2; r.in_es = 1;
+            r.out_qs = N; r.out_is = 1; r.out_es = (int)N1;
+            r.in_mode = MODE_ROW; r.out_mode = MODE_COL;
+            if (inv) { r.ld_flags = LD_CONJ; r.st_flags = ST_CONJ | ST_SCALE; r.scale = 1.0 / (double)N2; }
+            GD_TRY(launch_pass(d, l2, r, st));
+            continue;
+        }
         GD_TRY(fft_axis(d, src, tmp, 1, N1, N2, dir, st));                       // (1) columns: lines over n1, stride N2
         GD_TRY(fourstep_twiddle(tmp, N1, N2, 0, 0, log2n, st, dir));             // (2)
         GD_TRY(fft1d(d, tmp, N2, tmp, N2, N2, N1, false, dir, st));              // (3) rows, in place
@@ -319,7 +360,9 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         p.scale = ops.scale; p.div = ops.div;
         return launch_pass(d, log2n, p, st);
     }
-    if (log2n > 24) return fft_pow2_huge(d, in, in_dist, out, out_dist, log2n, batch, ops, st);
+    if (log2n > 24 || (log2n >= d.huge_min_log2n && ops.ld_flags == 0 && ops.st_flags == 0) ||
+        (log2n >= d.huge_min_log2n && ops.ld_flags == LD_CONJ && ops.st_flags == (ST_CONJ | ST_SCALE)))
+        return fft_pow2_huge(d, in, in_dist, out, out_dist, log2n, batch, ops, st);
     const bool lean = !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
     if (d.use_tma && lean && log2n == 20 && !d.debug_alias) {
         const int lc = (ops.ld_flags & LD_CONJ) ? 1 : 0, sc = (ops.st_flags & ST_CONJ) ? 1 : 0;
@@ -333,7 +376,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
         const long long main = batch - batch % te->unit;
         if (main > 0 && te->rows_ok(in, in_dist, out, out_dist, main, lc, sc, scl)) {
-            GD_TRY(te->run(d, 0, (const cpx*)in, in_dist, out, out_dist, main, lc != 0, scl, st));
+            GD_TRY(te->run(d, 0, (const cpx*)in, in_dist, out, out_dist, main, lc != 0, scl, st, 0, 0));
             if (main == batch) return GD_OK;
             return fft_pow2(d, (const cpx*)in + main * in_dist, in_dist, out + main * out_dist, out_dist, log2n, batch - main, ops, st);
         }
@@ -825,12 +868,15 @@ static Status bluestein_fft(Device& d, const void* in, long long in_dist, cpx* o
         }
         return GD_OK;
     }
-    long long chunk = (long long)((64ull << 20) / ((size_t)la * sizeof(cpx)));
+    // chunks large enough for the two transforms' inner L2-sized blocks to rotate over the chunk streams: with 64 MiB chunks every
+    // launch carried ~10 us of HBM time and the GPU idled between them (n = 4095: 8.7 GS/s)
+    long long chunk = (long long)(d.bluestein_chunk_bytes / ((size_t)la * sizeof(cpx)));
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
     cpx* A;
     GD_TRY(d.ensure_scratch(SCR_A, (size_t)chunk * la * sizeof(cpx), (void**)&A));
     const bool inv = dir < 0;
+    L2Hold hold(d);                                        // one set-aside for every chunk's two transforms
     for (long long b0 = 0; b0 < batch; b0 += chunk) {
         long long nb = batch - b0 < chunk ? batch - b0 : chunk;
         const void* src = real_in ? (const void*)((const double*)in + b0 * in_dist) : (const void*)((const cpx*)in + b0 * in_dist);
@@ -988,7 +1034,7 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         const long long main = ctotal - ctotal % te->unit;
         if (main > 0 && te->cols_ok(src + cfirst, dst + cfirst, len, main, s)) {
             for (long long o = 0; o < outer; o++)
-                GD_TRY(te->run(d, 1, src + o * len * s + cfirst, s, dst + o * len * s + cfirst, s, main, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st));
+                GD_TRY(te->run(d, 1, src + o * len * s + cfirst, s, dst + o * len * s + cfirst, s, main, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st, 0, 0));
             if (main == ctotal) return GD_OK;
             col0 = cfirst + main; ncols = ctotal - main;            // the remainder: fewer columns than a phase, two-launch path below
         }

@@ -82,6 +82,7 @@ struct Device {
     void* scratch[SCR_NSLOTS] = {nullptr};
     size_t scratch_bytes[SCR_NSLOTS] = {0};
     size_t pass_scratch_budget = 1ull << 30;    // upper bound of the inter-pass scratch of the two-launch four-step path
+    size_t bluestein_chunk_bytes = 1ull << 30;  // padded sequences of one Bluestein chunk (between its two transforms)
     size_t l2_block_budget = 24ull << 20;       // inter-pass block of one chunk: small enough to stay in L2 between the passes
     bool fourstep_pipeline = false;             // sharded four-step: exchange of a column block behind the lines of the next (measured: no gain)
     int fourstep_pipeline_mb = 256;             // slab bytes per pipeline block
@@ -90,7 +91,7 @@ struct Device {
     bool pwelch_bulk = true;                    // L = 4096 float64: bulk-copy fed kernel (pwelch.cu)
     int chunk_streams = 2;                      // streams the chunks of one call rotate over (1 .. 1 + AUX_STREAMS)
     bool l2_block_window = true;                // persisting L2 window over the inter-pass blocks of a chunked call
-    bool l2_hold = false;                       // a chunked call is in flight: keep the set-aside between its launches
+    int l2_hold = 0;                            // depth of chunked calls in flight: keep the set-aside between their launches (L2Hold)
     bool wide_tiles = false;             // 512-thread tiles for L >= 1024
     int w32 = 2;                         // 1024-point lean passes: 32 points per thread (fft_w32.cuh); 0 = 16-point kernel
     bool debug_alias = false;            // timing experiment only: all transforms of a batch alias one buffer (results are garbage)
@@ -106,6 +107,10 @@ struct Device {
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)
     bool use_tma14 = true;               // 2^14-point lines (batched rows, columns of a 2^14-row matrix): fused kernel of fft_tma14.cuh
+    int huge_min_log2n = 22;             // plain forward / inverse transforms of at least 2^this points take the outer four-step (fft_pow2_huge):
+                                         // from 2^22 on a 4096-point strided line pass reads one 16-byte element per 64 KiB row (6-23 GS/s)
+    int huge_l1 = 0;                     // measurement: log2 of the column length of that outer four-step (0 = the rule in fft_pow2_huge)
+    int huge_sweeps = 0;                 // measurement / cross-check: 3 or 4 forces the three- / four-sweep formulation
     int tma_grid_cap = 0;                // fused size family: at most this many CTAs (0 = one per SM); leaves SMs to a concurrent kernel
     bool use_tma16 = true;               // 2^16-point lines: the same kernel with 256-point sub-lines
     int tma_opt = 0;                     // measurement switches of the fused kernel (TmaFusedParams::opt)

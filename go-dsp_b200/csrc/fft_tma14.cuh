@@ -21,6 +21,9 @@
 // exchange, 32 / NJ butterflies of radix NJ. For LEN = 128 j is warp-uniform and the twiddles come from the kernel
 // parameters; otherwise they are a product chain from w_LEN^j.
 // PROF: cycle counters of the consumer groups (tools/exp_fft2_axes.py --prof only).
+// TW2 (COLS only): the lines are the length-N1 columns of ONE transform of M = N1 x N2 points laid out as [N1][N2]; output k1 of
+// column n2 leaves multiplied by w_M^(n2 k1), so the outer four-step's twiddle sweep disappears (fft_pow2_huge in engine.cu).
+// The three bases per thread and tile come from sincospi of exactly reduced exponents (no table above 2^24 entries).
 #pragma once
 #include <type_traits>
 #include "fft_tma.cuh"
@@ -67,6 +70,8 @@ struct Tma14Params {
     const cpx* wla;              // exp(-2 pi i p / LA), p < LA
     const cpx* wlb;              // exp(-2 pi i p / LB)
     long long* prof;             // measurement: [gridDim.x][TMA_PROF_SLOTS] cycle counters (null in the product)
+    int tw2_log2m;               // TW2 (COLS): the stores of pass 2 carry an outer four-step twiddle w_M^(column * k), M = 2^tw2_log2m,
+    long long tw2_col0;          //   column = tw2_col0 + the column's index in this launch, k = the output index in the line
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned long long* bar) {
@@ -96,7 +101,7 @@ __device__ __forceinline__ void t14_coords(int type, int grp, int c, int h, int 
     }
 }
 
-template <int LA, int LB, int MODE, bool INV, bool PROF>
+template <int LA, int LB, int MODE, bool INV, bool PROF, bool TW2 = false>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_int,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ Tma14Params a) {
@@ -322,6 +327,23 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             tb32 = cmul(__ldg(a.tw_hi + (e32 >> 12)), __ldg(a.tw_lo + (e32 & 4095u)));
             if (INV) tb0 = make_double2(tb0.x * a.scale, tb0.y * a.scale);
         }
+        if constexpr (TW2 && MODE == T14_COLS) {
+            if (wi.type == 1) {
+                // outer twiddle of this line's outputs k = k1 + LA k2, k2 = KB j' + k_lo + 32 m: w^(col (k1 + LA KB j')), w^(col LA), w^(32 col LA)
+                const unsigned long long mask = (1ULL << a.tw2_log2m) - 1ULL;
+                const unsigned long long col = (unsigned long long)a.tw2_col0 +
+                                               (unsigned long long)(wi.tf * SH::UNIT + (wi.c / LB) * SH::LINES_A + (ell % SH::LINES_A));
+                const unsigned long long k1 = (unsigned long long)((wi.c % LB) * SH::RA + ell / SH::LINES_A);
+                const double sc2 = 2.0 / (double)(1ULL << a.tw2_log2m);
+                double sn, cs;
+                sincospi((double)((col * (k1 + (unsigned long long)(LA * KB * j))) & mask) * sc2, &sn, &cs);
+                tb0 = make_double2(cs, -sn);
+                sincospi((double)((col * (unsigned long long)LA) & mask) * sc2, &sn, &cs);
+                tb1 = make_double2(cs, -sn);
+                sincospi((double)((col * (unsigned long long)(32 * LA)) & mask) * sc2, &sn, &cs);
+                tb32 = make_double2(cs, -sn);
+            }
+        }
         if (PROF) t0 = clock64();
         group_bar(1 + g);
         if (PROF) c_bar += clock64() - t0;
@@ -365,6 +387,20 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     for (int m = 0; m < NJ; m++) s[(kl + 32 * m) * LINES] = x[NJ * kl + m];
             }
         } else {
+            if constexpr (TW2 && MODE == T14_COLS) {
+                cpx c[KB];
+                c[0] = tb0;
+#pragma unroll
+                for (int kl = 1; kl < KB; kl++) c[kl] = cmul(c[kl - 1], tb1);
+#pragma unroll
+                for (int m = 0; m < NJ; m++) {
+#pragma unroll
+                    for (int kl = 0; kl < KB; kl++) {
+                        x[NJ * kl + m] = cmul(x[NJ * kl + m], c[kl]);
+                        if (m < NJ - 1) c[kl] = cmul(c[kl], tb32);
+                    }
+                }
+            }
             cpx* s = wbuf + (KB * j) * LINES + ell;          // X[k2 = KB j + k_lo + 32 m]: row k2 of the tile, column = line
 #pragma unroll
             for (int kl = 0; kl < KB; kl++)

@@ -55,11 +55,11 @@ static bool tma2d_cols_applicable(const cpx* src, const cpx* dst, long long len,
            ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
 }
 
-template <int LA, int LB, int MODE, bool INV, bool PROF = false>
+template <int LA, int LB, int MODE, bool INV, bool PROF = false, bool TW2 = false>
 static cudaError_t launch14(int grid, const CUtensorMap& mx, const CUtensorMap& mi, const CUtensorMap& mo, const Tma14Params& f, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(fft_tma14_kernel<LA, LB, MODE, INV, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, T14_SMEM);   // per device
+    cudaError_t e = cudaFuncSetAttribute(fft_tma14_kernel<LA, LB, MODE, INV, PROF, TW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T14_SMEM);   // per device
     if (e != cudaSuccess) return e;
-    fft_tma14_kernel<LA, LB, MODE, INV, PROF><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f);
+    fft_tma14_kernel<LA, LB, MODE, INV, PROF, TW2><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f);
     return cudaGetLastError();
 }
 
@@ -67,10 +67,11 @@ static inline cuuint64_t clamp_stride(unsigned long long v) { return v < (1ULL <
 
 // mode ROWS: `count` transforms of N = LA * LB points, transform t at in + t * in_dist / out + t * out_dist (count % UNIT == 0).
 // mode COLS: the first `count` columns of a row-major matrix with N rows (count % UNIT == 0): every column is a transform;
-//            in_dist = out_dist = the row pitch of the matrix in elements.
+//            in_dist = out_dist = the row pitch of the matrix in elements. tw2_log2m > 0: output k of column c leaves multiplied by
+//            w_M^((tw2_col0 + c) k), M = 2^tw2_log2m (conjugated for inv): the twiddle of an outer four-step over these lines.
 template <int LA, int LB>
 static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
-                         cudaStream_t st) {
+                         cudaStream_t st, int tw2_log2m, long long tw2_col0) {
     using SH = T14Shape<LA, LB>;
     constexpr cuuint64_t A = LA, Bq = LB, N = SH::N, LNA = SH::LINES_A, LNB = SH::LINES_B, UNIT = SH::UNIT;
     TmaEncodeFn14 enc;
@@ -86,6 +87,7 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
     int* cnt;
     GD_TRY(d.ensure_scratch(SCR_CNT, (2 * (size_t)CH + 2) * sizeof(int), (void**)&cnt));
     CUtensorMap m_int;
+    if (tw2_log2m && (mode != T14_COLS || LB > 256 || tw2_log2m < 0 || tw2_log2m > 40)) return invalid14("fused kernel: the outer twiddle needs column mode");
     if (mode == T14_ROWS) {
         // Int[t][n2][k1], t < UNIT * S: a pass-2 tile is LINES_B adjacent k1 x LB / 2 rows n2 per half
         const cuuint64_t dims[4] = {2 * A, Bq, UNIT * (cuuint64_t)S, 1};
@@ -153,6 +155,7 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         f.batch = (int)ng; f.delay = D; f.nslots = S; f.scratch = scratch;
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.scale = scale;
+        f.tw2_log2m = tw2_log2m; f.tw2_col0 = tw2_col0 + g0 * (long long)UNIT;
         f.prof = nullptr;
         if (d.tma_prof) {
             long long* pr;
@@ -166,7 +169,8 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         const int sms = d.tma_grid_cap > 0 && d.tma_grid_cap < d.num_sms ? d.tma_grid_cap : d.num_sms;
         const int grid = (int)(nitems < sms ? nitems : sms);
         if constexpr (LB <= 256) {
-            if (f.prof && !inv && LA == LB) e = mode == T14_ROWS ? launch14<LA, LB, T14_ROWS, false, LA == LB>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, LA == LB>(grid, m_x, m_int, m_out, f, st);
+            if (tw2_log2m) e = inv ? launch14<LA, LB, T14_COLS, true, false, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, false, true>(grid, m_x, m_int, m_out, f, st);
+            else if (f.prof && !inv && LA == LB) e = mode == T14_ROWS ? launch14<LA, LB, T14_ROWS, false, LA == LB>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, LA == LB>(grid, m_x, m_int, m_out, f, st);
             else if (mode == T14_ROWS) e = inv ? launch14<LA, LB, T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
             else e = inv ? launch14<LA, LB, T14_COLS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false>(grid, m_x, m_int, m_out, f, st);
         } else {
@@ -193,8 +197,8 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         return tma2d_cols_applicable<LA, LB>(src, dst, len, ncols, pitch);                                                              \
     }                                                                                                                                   \
     Status fft_tma_2p##LG(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, \
-                          double scale, cudaStream_t st) {                                                                              \
-        return fft_tma_2d<LA, LB>(d, mode, in, in_dist, out, out_dist, count, inv, scale, st);                                          \
+                          double scale, cudaStream_t st, int tw2_log2m, long long tw2_col0) {                                           \
+        return fft_tma_2d<LA, LB>(d, mode, in, in_dist, out, out_dist, count, inv, scale, st, tw2_log2m, tw2_col0);                     \
     }
 
 }  // namespace gd

@@ -98,6 +98,37 @@ def test_pow2_sizes(gd, lg):
     assert rel_l2(godsp.fft.IFFT(x), oracle.ifft(x)) <= TOL
 
 
+@pytest.mark.parametrize("lg", [21, 22, 23, 24, 25])
+def test_pow2_sizes_large(gd, lg):               # single transforms of 2^21 .. 2^25 points: outer four-step over the fused family
+    godsp, capi, L = gd
+    n = 1 << lg
+    x = oracle.splitmix_complex(n, 1)
+    want = oracle.fft(x)
+
+    def both():
+        assert rel_l2(godsp.fft.FFT(x), want) <= TOL
+        assert rel_l2(godsp.fft.IFFT(want), x) <= TOL
+
+    capi.check(L.gd_set_option(b"huge_min_log2n", 21))
+    try:
+        both()                                              # two sweeps: columns with the twiddle on their stores, rows with the transposed store
+        for l1 in (13, 14, 15, 17):                         # every column length of the family
+            capi.check(L.gd_set_option(b"huge_l1", l1))
+            assert rel_l2(godsp.fft.FFT(x), want) <= TOL
+        capi.check(L.gd_set_option(b"huge_l1", 0))
+        for sweeps in (3, 4):                               # columns, transpose, columns / columns, twiddle, rows, transpose
+            capi.check(L.gd_set_option(b"huge_sweeps", sweeps))
+            both()
+        capi.check(L.gd_set_option(b"huge_sweeps", 0))
+        if lg <= 24:
+            capi.check(L.gd_set_option(b"huge_min_log2n", 25))  # and the two-pass schedule
+            both()
+    finally:
+        capi.check(L.gd_set_option(b"huge_sweeps", 0))
+        capi.check(L.gd_set_option(b"huge_l1", 0))
+        capi.check(L.gd_set_option(b"huge_min_log2n", 22))
+
+
 @pytest.mark.parametrize("n", [1, 3, 5, 6, 7, 9, 12, 100, 255, 1000, 4097, 65537, 100003, 1000003])
 def test_bluestein_sizes(gd, n):                 # config C2 is n = 1,000,003 (la = 2^21)
     godsp = gd[0]

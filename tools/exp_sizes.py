@@ -17,6 +17,8 @@ y = torch.empty_like(x)
 capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), TOTAL * 2, 3, 0, None)); capi.check(L.gd_stream_sync(None))
 st = torch.cuda.Stream(); sp = st.cuda_stream
 args = sys.argv[1:]
+ONE = "--one" in args          # a single transform per call (latency of one large transform) instead of 2^28 points
+args = [a for a in args if a != "--one"]
 opts = ""
 if args and "=" in args[0]:
     opts = args.pop(0)
@@ -25,7 +27,7 @@ if args and "=" in args[0]:
 sizes = [int(a[1:]) if a.startswith("n") else 1 << int(a) for a in args] or [1 << k for k in range(8, 25)] + [1000, 4095, 100003, 1000003]
 import time
 for n in sizes:
-    batch = max(1, TOTAL // n)
+    batch = 1 if ONE else max(1, TOTAL // n)
     fn = lambda: capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, batch, 1, sp))
     torch.cuda.synchronize()
     with torch.cuda.stream(st):
