@@ -26,20 +26,23 @@ int pass32_tile_lines(int variant);
                                    int st_conj, double scale);                                                                           \
     bool tma##LG##_cols_applicable(const cpx* src, const cpx* dst, long long len, long long ncols, long long pitch);                     \
     Status fft_tma_2p##LG(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, \
-                          double scale, cudaStream_t st, int tw2_log2m, long long tw2_col0);
-GD_TMA2D_DECL(13) GD_TMA2D_DECL(14) GD_TMA2D_DECL(15) GD_TMA2D_DECL(16) GD_TMA2D_DECL(17) GD_TMA2D_DECL(18)
+                          double scale, cudaStream_t st, int tw2_log2m, long long tw2_col0, long long nmat, long long in_mdist,         \
+                          long long out_mdist);
+GD_TMA2D_DECL(13) GD_TMA2D_DECL(14) GD_TMA2D_DECL(15) GD_TMA2D_DECL(16) GD_TMA2D_DECL(17) GD_TMA2D_DECL(18) GD_TMA2D_DECL(19)
 struct Tma2dEntry {
     bool (*rows_ok)(const void*, long long, const cpx*, long long, long long, int, int, double);
     bool (*cols_ok)(const cpx*, const cpx*, long long, long long, long long);
-    Status (*run)(Device&, int, const cpx*, long long, cpx*, long long, long long, bool, double, cudaStream_t, int, long long);
+    Status (*run)(Device&, int, const cpx*, long long, cpx*, long long, long long, bool, double, cudaStream_t, int, long long, long long, long long,
+                  long long);
     int unit;                                            // transforms / columns per phase: 2^20 / N
 };
 static const Tma2dEntry* tma2d_entry(const Device& d, int log2n) {
-    static const Tma2dEntry tab[6] = {
+    static const Tma2dEntry tab[7] = {
         {tma13_rows_applicable, tma13_cols_applicable, fft_tma_2p13, 128}, {tma14_rows_applicable, tma14_cols_applicable, fft_tma_2p14, 64},
         {tma15_rows_applicable, tma15_cols_applicable, fft_tma_2p15, 32},  {tma16_rows_applicable, tma16_cols_applicable, fft_tma_2p16, 16},
-        {tma17_rows_applicable, tma17_cols_applicable, fft_tma_2p17, 8},   {tma18_rows_applicable, tma18_cols_applicable, fft_tma_2p18, 4}};
-    if (!d.use_tma || log2n < 13 || log2n > 18) return nullptr;
+        {tma17_rows_applicable, tma17_cols_applicable, fft_tma_2p17, 8},   {tma18_rows_applicable, tma18_cols_applicable, fft_tma_2p18, 4},
+        {tma19_rows_applicable, tma19_cols_applicable, fft_tma_2p19, 2}};
+    if (!d.use_tma || log2n < 13 || log2n > 19 || (log2n == 19 && !d.use_tma19)) return nullptr;
     if (log2n == 14 ? !d.use_tma14 : !d.use_tma16) return nullptr;       // "tma14": the 2^14 kernel; "tma16": every other size of the family
     return &tab[log2n - 13];
 }
@@ -301,8 +304,6 @@ static Status fft_pow2_huge(Device& d, const void* in, long long in_dist, cpx* o
     if (log2n > 34) return invalid("fft_pow2: N > 2^34");
     const int dir = inv ? -1 : +1;
     const long long N = 1LL << log2n;
-    cpx* tmp;
-    GD_TRY(d.ensure_scratch(SCR_HUGE, (size_t)N * sizeof(cpx), (void**)&tmp));
     // the split: N1 through the fused family in column mode (2^13 .. 2^17 rows), N2 = N / N1
     int l1 = d.huge_l1 ? d.huge_l1 : (log2n <= 24 ? 16 : log2n <= 29 ? 17 : (log2n + 1) / 2);
     if (l1 > log2n - 4) l1 = log2n - 4;
@@ -312,15 +313,40 @@ static Status fft_pow2_huge(Device& d, const void* in, long long in_dist, cpx* o
     if (te && !three && l2 > 12) te = nullptr;
     if (!te) { l1 = (log2n + 1) / 2; l2 = log2n - l1; }
     const long long N1 = 1LL << l1, N2 = 1LL << l2;
+    // two sweeps: the transforms of a batch go through each sweep together, as many as fit the scratch budget (one launch per sweep
+    // instead of one per transform: at 2^21 .. 2^23 points a launch per transform is mostly ramp and tail)
+    long long per = 1;
+    if (te && !three && batch > 1 && N2 / te->unit <= 512 && in_dist < (1LL << 35)) {
+        per = (long long)(d.pass_scratch_budget / ((size_t)N * sizeof(cpx)));
+        if (per < 1) per = 1;
+        if (per > batch) per = batch;
+    }
+    cpx* tmp;
+    GD_TRY(d.ensure_scratch(SCR_HUGE, (size_t)per * N * sizeof(cpx), (void**)&tmp));
     // the fused kernel's persisting L2 set-aside stays carved across the sweeps and the transforms of the batch (handing it back and
     // carving it again around every pass kernel costs more host time than a 2^21-point transform takes)
     L2Hold hold(d);
+    if (per > 1 && te->cols_ok((const cpx*)in, tmp, N1, N2, N2)) {
+        for (long long b0 = 0; b0 < batch; b0 += per) {
+            const long long nb = batch - b0 < per ? batch - b0 : per;
+            GD_TRY(te->run(d, 1, (const cpx*)in + b0 * in_dist, N2, tmp, N2, N2, inv, inv ? 1.0 / (double)N1 : 1.0, st, log2n, 0, nb, in_dist, N));
+            PassParams r = base_params(d, l2);
+            r.in = tmp; r.out = out + b0 * out_dist;
+            r.nlines = nb * N1; r.inner = N1;
+            r.in_qs = N; r.in_is = N2; r.in_es = 1;
+            r.out_qs = out_dist; r.out_is = 1; r.out_es = (int)N1;
+            r.in_mode = MODE_ROW; r.out_mode = MODE_COL;
+            if (inv) { r.ld_flags = LD_CONJ; r.st_flags = ST_CONJ | ST_SCALE; r.scale = 1.0 / (double)N2; }
+            GD_TRY(launch_pass(d, l2, r, st));
+        }
+        return GD_OK;
+    }
     for (long long b = 0; b < batch; b++) {
         const cpx* src = (const cpx*)in + b * in_dist;
         cpx* dst = out + b * out_dist;
         if (te && te->cols_ok(src, tmp, N1, N2, N2)) {
             cpx* mid = three ? dst : tmp;                                        // three sweeps: columns -> dst, transpose -> tmp, columns -> dst
-            GD_TRY(te->run(d, 1, src, N2, mid, N2, N2, inv, inv ? 1.0 / (double)N1 : 1.0, st, log2n, 0));   // (1) columns n2, twiddle on store
+            GD_TRY(te->run(d, 1, src, N2, mid, N2, N2, inv, inv ? 1.0 / (double)N1 : 1.0, st, log2n, 0, 1, 0, 0));   // (1) columns n2, twiddle on store
             if (three) {
                 GD_TRY(transpose_batched(mid, tmp, 1, N1, N2, st));              // (2) [N1][N2] -> [N2][N1]
                 GD_TRY(fft_axis(d, tmp, dst, 1, N2, N1, dir, st));               // (3) lines over n2 at stride N1
@@ -360,8 +386,10 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         p.scale = ops.scale; p.div = ops.div;
         return launch_pass(d, log2n, p, st);
     }
-    if (log2n > 24 || (log2n >= d.huge_min_log2n && ops.ld_flags == 0 && ops.st_flags == 0) ||
-        (log2n >= d.huge_min_log2n && ops.ld_flags == LD_CONJ && ops.st_flags == (ST_CONJ | ST_SCALE)))
+    // plain forward / inverse transforms from 2^22 points (2^21 in a batch, where every sweep is one launch over the batch) take the outer four-step
+    const int hmin = batch > 1 ? d.huge_min_log2n - 1 : d.huge_min_log2n;
+    if (log2n > 24 || (log2n >= hmin && ops.ld_flags == 0 && ops.st_flags == 0) ||
+        (log2n >= hmin && ops.ld_flags == LD_CONJ && ops.st_flags == (ST_CONJ | ST_SCALE)))
         return fft_pow2_huge(d, in, in_dist, out, out_dist, log2n, batch, ops, st);
     const bool lean = !(ops.ld_flags & ~LD_CONJ) && !(ops.st_flags & ~(ST_CONJ | ST_SCALE));
     if (d.use_tma && lean && log2n == 20 && !d.debug_alias) {
@@ -376,7 +404,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
         const long long main = batch - batch % te->unit;
         if (main > 0 && te->rows_ok(in, in_dist, out, out_dist, main, lc, sc, scl)) {
-            GD_TRY(te->run(d, 0, (const cpx*)in, in_dist, out, out_dist, main, lc != 0, scl, st, 0, 0));
+            GD_TRY(te->run(d, 0, (const cpx*)in, in_dist, out, out_dist, main, lc != 0, scl, st, 0, 0, 1, 0, 0));
             if (main == batch) return GD_OK;
             return fft_pow2(d, (const cpx*)in + main * in_dist, in_dist, out + main * out_dist, out_dist, log2n, batch - main, ops, st);
         }
@@ -1034,7 +1062,7 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         const long long main = ctotal - ctotal % te->unit;
         if (main > 0 && te->cols_ok(src + cfirst, dst + cfirst, len, main, s)) {
             for (long long o = 0; o < outer; o++)
-                GD_TRY(te->run(d, 1, src + o * len * s + cfirst, s, dst + o * len * s + cfirst, s, main, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st, 0, 0));
+                GD_TRY(te->run(d, 1, src + o * len * s + cfirst, s, dst + o * len * s + cfirst, s, main, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st, 0, 0, 1, 0, 0));
             if (main == ctotal) return GD_OK;
             col0 = cfirst + main; ncols = ctotal - main;            // the remainder: fewer columns than a phase, two-launch path below
         }

@@ -107,11 +107,13 @@ struct Device {
     size_t fused_slot_budget = 16ull << 20;   // bytes of L2-resident intermediate per scratch slot (fused_delay + 2 slots)
     bool use_tma = true;                 // N = 2^20 lean transforms: TMA-fed fused four-step, intermediate resident in L2 (fft_tma.cuh)
     bool use_tma14 = true;               // 2^14-point lines (batched rows, columns of a 2^14-row matrix): fused kernel of fft_tma14.cuh
-    int huge_min_log2n = 22;             // plain forward / inverse transforms of at least 2^this points take the outer four-step (fft_pow2_huge):
-                                         // from 2^22 on a 4096-point strided line pass reads one 16-byte element per 64 KiB row (6-23 GS/s)
+    int huge_min_log2n = 22;             // plain forward / inverse transforms of at least 2^this points (one less in a batch) take the outer
+                                         // four-step over the fused family (fft_pow2_huge): two sweeps at 0.30-0.37 of HBM, where the 4096-point
+                                         // strided line passes of the two-launch schedule fall to 6-23 GS/s
     int huge_l1 = 0;                     // measurement: log2 of the column length of that outer four-step (0 = the rule in fft_pow2_huge)
     int huge_sweeps = 0;                 // measurement / cross-check: 3 or 4 forces the three- / four-sweep formulation
     int tma_grid_cap = 0;                // fused size family: at most this many CTAs (0 = one per SM); leaves SMs to a concurrent kernel
+    bool use_tma19 = true;               // 2^19-point transforms: the same kernel with 1024-point pass-1 sub-lines (rows only)
     bool use_tma16 = true;               // 2^16-point lines: the same kernel with 256-point sub-lines
     int tma_opt = 0;                     // measurement switches of the fused kernel (TmaFusedParams::opt)
     int tma_prof = 0;                    // measurement: cycle counters of the fused kernel (gd_tma_profile_read)

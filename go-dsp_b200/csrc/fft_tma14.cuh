@@ -1,4 +1,4 @@
-// fft_tma14.cuh -- complex128 transforms of N = LA x LB points, 2^13 <= N <= 2^18 (LA, LB in {64, 128, 256, 512}, LA >= LB), as
+// fft_tma14.cuh -- complex128 transforms of N = LA x LB points, 2^13 <= N <= 2^19 (LA, LB in {64, 128, 256, 512}, LA >= LB; 2^19 = 1024 x 512, rows only), as
 // ONE persistent, TMA-fed launch: both passes of the four-step, intermediate resident in L2. N = 2^14 = 128 x 128 are the
 // lines of fft.FFT2 on a 16384 x 16384 matrix (config C3); N = 2^16 = 256 x 256 the local lines of the sharded 2^32-point
 // transform (config C5). Same machinery as fft_tma.cuh (in-order tile queue, loader / storer / watcher lanes, D = 2 phases
@@ -32,11 +32,11 @@ namespace gd {
 
 template <int LEN>
 struct T14Len {
-    static_assert(LEN == 64 || LEN == 128 || LEN == 256 || LEN == 512, "sub-line length");
-    static constexpr int LINES = 4096 / LEN;                          // lines per tile: 64 / 32 / 16 / 8
-    static constexpr int NJ = LEN / 32;                               // residues of the point index held by different threads: 2 / 4 / 8 / 16
+    static_assert(LEN == 64 || LEN == 128 || LEN == 256 || LEN == 512 || LEN == 1024, "sub-line length");
+    static constexpr int LINES = 4096 / LEN;                          // lines per tile: 64 / 32 / 16 / 8 / 4
+    static constexpr int NJ = LEN / 32;                               // residues of the point index held by different threads: 2 / 4 / 8 / 16 / 32
     static constexpr int KB = 32 / NJ;                                // outputs k = KB j' + k_lo + 32 m per thread
-    static constexpr int LOG2 = LEN == 64 ? 6 : LEN == 128 ? 7 : LEN == 256 ? 8 : 9;
+    static constexpr int LOG2 = LEN == 64 ? 6 : LEN == 128 ? 7 : LEN == 256 ? 8 : LEN == 512 ? 9 : 10;
 };
 template <int LA, int LB>
 struct T14Shape {
@@ -72,6 +72,7 @@ struct Tma14Params {
     long long* prof;             // measurement: [gridDim.x][TMA_PROF_SLOTS] cycle counters (null in the product)
     int tw2_log2m;               // TW2 (COLS): the stores of pass 2 carry an outer four-step twiddle w_M^(column * k), M = 2^tw2_log2m,
     long long tw2_col0;          //   column = tw2_col0 + the column's index in this launch, k = the output index in the line
+    int bshift;                  // COLS: a launch over several matrices (dimension 3 of the maps) has 2^bshift phases per matrix; 31 = one matrix
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned long long* bar) {
@@ -85,7 +86,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c0, int 
 
 // tile c of phase (type, grp), half h -> tensor coordinates (in doubles along dim 0); in: the load side (pass 2 reads Int)
 template <int LA, int LB, int MODE>
-__device__ __forceinline__ void t14_coords(int type, int grp, int c, int h, int S, int& c0, int& c1, int& c2, int& c3, bool in) {
+__device__ __forceinline__ void t14_coords(int type, int grp, int c, int h, int S, int bshift, int& c0, int& c1, int& c2, int& c3, bool in) {
     using SH = T14Shape<LA, LB>;
     if constexpr (MODE == T14_ROWS) {
         const int tl = c / SH::TPT, q = c % SH::TPT;      // transform within the group, block of LINES lines
@@ -95,9 +96,10 @@ __device__ __forceinline__ void t14_coords(int type, int grp, int c, int h, int 
         else { c0 = 2 * SH::LINES_B * q; c1 = (LB / 2) * h; }
     } else {
         const int tbl = c / LB, r = c % LB;               // column block within the group; n2 (pass 1) or k1 group (pass 2)
-        if (type == 0) { c0 = 2 * (grp * SH::UNIT + tbl * SH::LINES_A); c1 = r; c2 = (LA / 2) * h; c3 = 0; }
+        const int mat = grp >> bshift, gl = grp & (int)((1u << bshift) - 1u);      // matrix of the launch, phase within the matrix
+        if (type == 0) { c0 = 2 * (gl * SH::UNIT + tbl * SH::LINES_A); c1 = r; c2 = (LA / 2) * h; c3 = mat; }
         else if (in) { c0 = 0; c1 = r * SH::RA; c2 = (LB / 2) * h; c3 = (grp % S) * SH::TBP + tbl; }
-        else { c0 = 2 * (grp * SH::UNIT + tbl * SH::LINES_A); c1 = r * SH::RA; c2 = (LB / 2) * h; c3 = 0; }
+        else { c0 = 2 * (gl * SH::UNIT + tbl * SH::LINES_A); c1 = r * SH::RA; c2 = (LB / 2) * h; c3 = mat; }
     }
 }
 
@@ -170,7 +172,15 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     if (token) { mbar_arrive(fb); continue; }
                     mbar_expect_tx(fb, T14_HALF_BYTES);
                     int c0, c1, c2, c3;
-                    t14_coords<LA, LB, MODE>(w.type, w.tf, w.c, h, S, c0, c1, c2, c3, true);
+                    t14_coords<LA, LB, MODE>(w.type, w.tf, w.c, h, S, a.bshift, c0, c1, c2, c3, true);
+                    if constexpr (LA == 1024) {
+                        // a box has at most 256 rows: the 512 rows of a pass-1 half arrive as two copies on the same barrier
+                        if (w.type == 0) {
+                            tma_load_4d(land + (size_t)s * HALF_ELEMS, &tm_x, c0, c1, c2, c3, fb);
+                            tma_load_4d(land + (size_t)s * HALF_ELEMS + HALF_ELEMS / 2, &tm_x, c0, c1 + 256, c2, c3, fb);
+                            continue;
+                        }
+                    }
                     tma_load_4d(land + (size_t)s * HALF_ELEMS, w.type == 0 ? &tm_x : &tm_int, c0, c1, c2, c3, fb);
                 }
                 if (!tokens && (it & 1)) cur = atomicAdd(a.queue, 2);
@@ -204,10 +214,10 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 const cpx* srcb = work + (size_t)g * T14_WELEMS;
                 if (pi.type == 1) {
                     int c0, c1, c2, c3;
-                    t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, 0, S, c0, c1, c2, c3, false);
+                    t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, 0, S, a.bshift, c0, c1, c2, c3, false);
                     tma_store_4d(&tm_out, c0, c1, c2, c3, srcb);
                     tma_commit();
-                    t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, 1, S, c0, c1, c2, c3, false);
+                    t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, 1, S, a.bshift, c0, c1, c2, c3, false);
                     tma_store_4d(&tm_out, c0, c1, c2, c3, srcb + HALF_ELEMS);
                     tma_commit();
                 } else {
@@ -332,7 +342,7 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 // outer twiddle of this line's outputs k = k1 + LA k2, k2 = KB j' + k_lo + 32 m: w^(col (k1 + LA KB j')), w^(col LA), w^(32 col LA)
                 const unsigned long long mask = (1ULL << a.tw2_log2m) - 1ULL;
                 const unsigned long long col = (unsigned long long)a.tw2_col0 +
-                                               (unsigned long long)(wi.tf * SH::UNIT + (wi.c / LB) * SH::LINES_A + (ell % SH::LINES_A));
+                                               (unsigned long long)((wi.tf & (int)((1u << a.bshift) - 1u)) * SH::UNIT + (wi.c / LB) * SH::LINES_A + (ell % SH::LINES_A));
                 const unsigned long long k1 = (unsigned long long)((wi.c % LB) * SH::RA + ell / SH::LINES_A);
                 const double sc2 = 2.0 / (double)(1ULL << a.tw2_log2m);
                 double sn, cs;
@@ -353,24 +363,30 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             for (int r = 0; r < 32; r++) x[r] = s[r * LINES];                                // x[NJ k_lo + jj] = Y_jj[KB j + k_lo]
         }
         mbar_arrive(rd + g);
+        if constexpr (NJ == 32) dft32(x);
+        else {
 #pragma unroll
-        for (int kl = 0; kl < KB; kl++) dft<NJ, 1>(&x[NJ * kl]);                             // x[NJ k_lo + m] = X[KB j + k_lo + 32 m]
+            for (int kl = 0; kl < KB; kl++) dft<NJ, 1>(&x[NJ * kl]);                         // x[NJ k_lo + m] = X[KB j + k_lo + 32 m]
+        }
         if (PROF) t0 = clock64();
         mbar_wait(rd + g, nrd & 1);                         // every gather of this tile is done: the buffer may be overwritten
         nrd++;
         if (PROF) c_rd += clock64() - t0;
         if (wi.type == 0) {
             // x[NJ k_lo + m] *= w^(n2 (KB j + k_lo + 32 m)) = tb0 * tb1^k_lo * tb32^m
-            cpx c[KB];
-            c[0] = tb0;
+            if constexpr (NJ == 32) mul_geometric32(x, tb0, tb32);
+            else {
+                cpx c[KB];
+                c[0] = tb0;
 #pragma unroll
-            for (int kl = 1; kl < KB; kl++) c[kl] = cmul(c[kl - 1], tb1);
+                for (int kl = 1; kl < KB; kl++) c[kl] = cmul(c[kl - 1], tb1);
 #pragma unroll
-            for (int m = 0; m < NJ; m++) {
+                for (int m = 0; m < NJ; m++) {
 #pragma unroll
-                for (int kl = 0; kl < KB; kl++) {
-                    x[NJ * kl + m] = cmul(x[NJ * kl + m], c[kl]);
-                    if (m < NJ - 1) c[kl] = cmul(c[kl], tb32);
+                    for (int kl = 0; kl < KB; kl++) {
+                        x[NJ * kl + m] = cmul(x[NJ * kl + m], c[kl]);
+                        if (m < NJ - 1) c[kl] = cmul(c[kl], tb32);
+                    }
                 }
             }
             if constexpr (MODE == T14_ROWS) {

@@ -69,9 +69,11 @@ static inline cuuint64_t clamp_stride(unsigned long long v) { return v < (1ULL <
 // mode COLS: the first `count` columns of a row-major matrix with N rows (count % UNIT == 0): every column is a transform;
 //            in_dist = out_dist = the row pitch of the matrix in elements. tw2_log2m > 0: output k of column c leaves multiplied by
 //            w_M^((tw2_col0 + c) k), M = 2^tw2_log2m (conjugated for inv): the twiddle of an outer four-step over these lines.
+//            nmat > 1: the same columns of nmat matrices (matrix m at in + m * in_mdist / out + m * out_mdist) in the same launches;
+//            count / UNIT must be a power of two <= 512 (the matrices ride on dimension 3 of the tensor maps).
 template <int LA, int LB>
 static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
-                         cudaStream_t st, int tw2_log2m, long long tw2_col0) {
+                         cudaStream_t st, int tw2_log2m, long long tw2_col0, long long nmat, long long in_mdist, long long out_mdist) {
     using SH = T14Shape<LA, LB>;
     constexpr cuuint64_t A = LA, Bq = LB, N = SH::N, LNA = SH::LINES_A, LNB = SH::LINES_B, UNIT = SH::UNIT;
     TmaEncodeFn14 enc;
@@ -131,31 +133,41 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         d.l2_dirty = true;
     }
     Status rc = GD_OK;
-    const long long groups = count / (long long)UNIT;
+    const long long gpm = count / (long long)UNIT;                     // phases per matrix
+    int bshift = 31;
+    if (nmat > 1) {
+        if (mode != T14_COLS || gpm > CH || (gpm & (gpm - 1)) || in_mdist >= (1LL << 35) || out_mdist >= (1LL << 35)) return invalid14("fused kernel: bad multi-matrix launch");
+        for (bshift = 0; (1LL << bshift) < gpm; bshift++) {}
+    } else nmat = 1;
+    const long long groups = gpm * nmat;
     for (long long g0 = 0; g0 < groups && rc == GD_OK; g0 += CH) {
         const long long ng = groups - g0 < CH ? groups - g0 : CH;
-        const cuuint64_t nt = (cuuint64_t)ng * UNIT;                   // transforms / columns of this launch
+        const bool multi = nmat > 1;
+        const long long m0 = multi ? g0 / gpm : 0;                     // first matrix of this launch
+        const cuuint64_t nm = multi ? (cuuint64_t)(ng / gpm) : 1;      // matrices of this launch (CH is a multiple of gpm)
+        const cuuint64_t nt = multi ? (cuuint64_t)count : (cuuint64_t)ng * UNIT;   // transforms / columns (per matrix) of this launch
         CUtensorMap m_x, m_out;
         if (mode == T14_ROWS) {
             const cuuint64_t dx[4] = {2 * Bq, A, nt, 1}, dout[4] = {2 * A, Bq, nt, 1};
-            const cuuint32_t bx[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)(A / 2), 1, 1}, bo[4] = {(cuuint32_t)(2 * LNB), (cuuint32_t)(Bq / 2), 1, 1};
+            const cuuint32_t bx[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)(A / 2 > 256 ? 256 : A / 2), 1, 1}, bo[4] = {(cuuint32_t)(2 * LNB), (cuuint32_t)(Bq / 2), 1, 1};
             const cuuint64_t sx[3] = {Bq * 16, (cuuint64_t)in_dist * 16, clamp_stride((cuuint64_t)in_dist * 16 * nt)};
             const cuuint64_t so[3] = {A * 16, (cuuint64_t)out_dist * 16, clamp_stride((cuuint64_t)out_dist * 16 * nt)};
             if ((rc = map4(enc, in + g0 * (long long)UNIT * in_dist, dx, sx, bx, &m_x)) != GD_OK) break;
             if ((rc = map4(enc, out + g0 * (long long)UNIT * out_dist, dout, so, bo, &m_out)) != GD_OK) break;
         } else {
             const cuuint64_t pi_ = (cuuint64_t)in_dist * 16, po = (cuuint64_t)out_dist * 16;
-            const cuuint64_t dx[4] = {2 * nt, Bq, A, 1}, dout[4] = {2 * nt, A, Bq, 1};
+            const cuuint64_t dx[4] = {2 * nt, Bq, A, nm}, dout[4] = {2 * nt, A, Bq, nm};
             const cuuint32_t bx[4] = {(cuuint32_t)(2 * LNA), 1, (cuuint32_t)(A / 2), 1}, bo[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)SH::RA, (cuuint32_t)(Bq / 2), 1};
-            const cuuint64_t sx[3] = {pi_, pi_ * Bq, clamp_stride(pi_ * N)};
-            const cuuint64_t so[3] = {po, po * A, clamp_stride(po * N)};
-            if ((rc = map4(enc, in + g0 * (long long)UNIT, dx, sx, bx, &m_x)) != GD_OK) break;
-            if ((rc = map4(enc, out + g0 * (long long)UNIT, dout, so, bo, &m_out)) != GD_OK) break;
+            const cuuint64_t sx[3] = {pi_, pi_ * Bq, multi ? (cuuint64_t)in_mdist * 16 : clamp_stride(pi_ * N)};
+            const cuuint64_t so[3] = {po, po * A, multi ? (cuuint64_t)out_mdist * 16 : clamp_stride(po * N)};
+            if ((rc = map4(enc, multi ? in + m0 * in_mdist : in + g0 * (long long)UNIT, dx, sx, bx, &m_x)) != GD_OK) break;
+            if ((rc = map4(enc, multi ? out + m0 * out_mdist : out + g0 * (long long)UNIT, dout, so, bo, &m_out)) != GD_OK) break;
         }
         f.batch = (int)ng; f.delay = D; f.nslots = S; f.scratch = scratch;
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.scale = scale;
-        f.tw2_log2m = tw2_log2m; f.tw2_col0 = tw2_col0 + g0 * (long long)UNIT;
+        f.tw2_log2m = tw2_log2m; f.tw2_col0 = multi ? tw2_col0 : tw2_col0 + g0 * (long long)UNIT;
+        f.bshift = bshift;
         f.prof = nullptr;
         if (d.tma_prof) {
             long long* pr;
@@ -197,8 +209,10 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         return tma2d_cols_applicable<LA, LB>(src, dst, len, ncols, pitch);                                                              \
     }                                                                                                                                   \
     Status fft_tma_2p##LG(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, \
-                          double scale, cudaStream_t st, int tw2_log2m, long long tw2_col0) {                                           \
-        return fft_tma_2d<LA, LB>(d, mode, in, in_dist, out, out_dist, count, inv, scale, st, tw2_log2m, tw2_col0);                     \
+                          double scale, cudaStream_t st, int tw2_log2m, long long tw2_col0, long long nmat, long long in_mdist,         \
+                          long long out_mdist) {                                                                                        \
+        return fft_tma_2d<LA, LB>(d, mode, in, in_dist, out, out_dist, count, inv, scale, st, tw2_log2m, tw2_col0, nmat, in_mdist,      \
+                                  out_mdist);                                                                                           \
     }
 
 }  // namespace gd

@@ -129,6 +129,20 @@ def test_pow2_sizes_large(gd, lg):               # single transforms of 2^21 .. 
         capi.check(L.gd_set_option(b"huge_min_log2n", 22))
 
 
+@pytest.mark.parametrize("lg,b", [(21, 5), (22, 3), (23, 2)])
+def test_pow2_large_batched(gd, lg, b):           # a batch of large transforms: every sweep of the outer four-step in one launch
+    godsp, capi, L = gd
+    n = 1 << lg
+    x = oracle.splitmix_complex(n * b, 2)
+    want = np.concatenate([oracle.fft(x[i * n:(i + 1) * n]) for i in range(b)])
+    try:
+        got = godsp.fft.FFTBatch(x, n)
+        assert max(rel_l2(got[i * n:(i + 1) * n], want[i * n:(i + 1) * n]) for i in range(b)) <= TOL
+        assert rel_l2(godsp.fft.FFTBatch(want, n, -1), x) <= TOL
+    finally:
+        capi.check(L.gd_set_option(b"huge_min_log2n", 22))
+
+
 @pytest.mark.parametrize("n", [1, 3, 5, 6, 7, 9, 12, 100, 255, 1000, 4097, 65537, 100003, 1000003])
 def test_bluestein_sizes(gd, n):                 # config C2 is n = 1,000,003 (la = 2^21)
     godsp = gd[0]
@@ -379,9 +393,9 @@ def test_fft2_fused_2p14_lines(gd, rows, cols):  # the fused 2^14 kernel (fft_tm
 
 
 @pytest.mark.parametrize("phases", [1, 2])
-@pytest.mark.parametrize("lg", [13, 14, 15, 16, 17, 18])
+@pytest.mark.parametrize("lg", [13, 14, 15, 16, 17, 18, 19])
 def test_fused_family_rows_and_columns(gd, lg, phases):
-    """The TMA-fed fused four-step (fft_tma14.cuh) for every size of its family, N = LA x LB = 2^13 .. 2^18: batched contiguous
+    """The TMA-fed fused four-step (fft_tma14.cuh) for every size of its family, N = LA x LB = 2^13 .. 2^19: batched contiguous
     transforms and the columns of an N-row matrix, forward and inverse, with a batch / column count that is not a multiple
     of a phase (the remainder goes through the two-launch path); sampled lines against the oracle, everything against the
     two-launch schedule."""
@@ -396,7 +410,7 @@ def test_fused_family_rows_and_columns(gd, lg, phases):
     xh = x.cpu().numpy().view(np.complex128)
     outs = {}
     for fused in (1, 0):
-        capi.check(L.gd_set_option(b"tma14", fused)); capi.check(L.gd_set_option(b"tma16", fused))
+        capi.check(L.gd_set_option(b"tma14", fused)); capi.check(L.gd_set_option(b"tma16", fused)); capi.check(L.gd_set_option(b"tma19", fused))
         try:
             y, z, yc, zc = (torch.empty_like(x) for _ in range(4))
             l0 = L.gd_kernel_launches()
@@ -421,7 +435,7 @@ def test_fused_family_rows_and_columns(gd, lg, phases):
             outs[fused] = (y.cpu().numpy().view(np.complex128), z.cpu().numpy().view(np.complex128),
                            yc.cpu().numpy().view(np.complex128) if ok_cols else None, zc.cpu().numpy().view(np.complex128) if ok_cols else None, nl_rows)
         finally:
-            capi.check(L.gd_set_option(b"tma14", 1)); capi.check(L.gd_set_option(b"tma16", 1))
+            capi.check(L.gd_set_option(b"tma14", 1)); capi.check(L.gd_set_option(b"tma16", 1)); capi.check(L.gd_set_option(b"tma19", 1))
     y, z, yc, zc, nl_fused = outs[1]
     y0, z0, yc0, zc0, nl_plain = outs[0]
     if phases == 2:
