@@ -1,5 +1,5 @@
 // bluestein_small.cuh -- a whole Bluestein transform (fft/bluestein.go:67-96) of a line in ONE kernel, for padded
-// lengths la <= 4096 (n <= 2048): chirp multiply and zero-pad on load, FFT_la, product with the cached FFT(b),
+// lengths la <= 8192 (n <= 4096): chirp multiply and zero-pad on load, FFT_la, product with the cached FFT(b),
 // inverse FFT_la as conj . FFT . conj with 1/la, chirp multiply, truncation to n -- the padded sequence never leaves
 // the SM. Memory traffic is the n inputs and n outputs of each line (32 B per point) instead of two la-point
 // transforms through memory; the arithmetic, operation by operation, is that of the two fft_pass_kernel<GENERIC>

@@ -111,7 +111,7 @@ Status Device::init(int device, int lane_index) {
     }
     GD_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     GD_CUDA(cudaEventCreateWithFlags(&ev_pipe, cudaEventDisableTiming));
-    for (int k = 5; k <= 12; k++) {
+    for (int k = 5; k <= 13; k++) {
         std::vector<cpx> h;
         host_twiddles(h, 1LL << k, 1, 1LL << k);
         GD_TRY(upload(h, &wl[k]));
@@ -861,7 +861,7 @@ static Status bluestein_fft(Device& d, const void* in, long long in_dist, cpx* o
     const BluesteinPlan* pl;
     GD_TRY(d.bluestein(n, st, &pl));
     const long long la = pl->la;
-    if (pl->log2la <= 12 && d.bluestein_fused) {
+    if (pl->log2la <= 13 && d.bluestein_fused) {
         // the whole transform of a line in one kernel, the padded sequence stays on the SM (bluestein_small.cuh)
         BluesteinSmallParams b;
         b.in = in; b.out = out; b.in_dist = in_dist; b.out_dist = out_dist; b.n = n; b.batch = batch;
@@ -1043,7 +1043,9 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
     if (s == 1) return fft1d(d, src, len, dst, len, len, outer, false, dir, st);
     const bool p2 = is_pow2(len);
     const bool fits31 = (double)len * (double)s < 2147483648.0;   // in-line offsets are 32-bit in the pass kernel
-    if (p2 && len <= 4096 && fits31) {
+    // one strided pass: T adjacent columns per tile, T x 16 contiguous bytes per row. 4096-point lines leave 32 bytes per row, so wide
+    // matrices take the blocked four-step below instead (FFT2 4096 x 16384: 2.19 -> 1.22 ms; 2048-point lines measured equal either way)
+    if (p2 && fits31 && !sub && (len <= (1LL << d.axis_single_max_log2) || (len <= 4096 && s < 64))) {
         int l = ilog2ll(len);
         PassParams p = base_params(d, l);
         p.in = src; p.out = dst; p.nlines = nlines; p.inner = s;
@@ -1052,8 +1054,8 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         if (dir < 0) { p.ld_flags = LD_CONJ; p.st_flags = ST_CONJ | ST_SCALE; p.scale = 1.0 / (double)len; }
         return launch_pass(d, l, p, st);
     }
-    if (sub && !(is_pow2(len) && len > 4096 && len <= (1LL << 24) && (double)len * (double)s < 2147483648.0))
-        return invalid("fft_axis: a column range needs a power-of-two length in (4096, 2^24]");
+    if (sub && !(p2 && len >= 4 && len <= (1LL << 24) && fits31))
+        return invalid("fft_axis: a column range needs a power-of-two length in [4, 2^24]");
     if (const Tma2dEntry* te = p2 ? tma2d_entry(d, ilog2ll(len)) : nullptr) {
         // columns of a matrix with 2^13 .. 2^17 rows (2^14: fft.FFT2 on 16384 x 16384; 2^16: the line passes of the sharded
         // 2^32-point transform): whole phases of columns in one fused launch, intermediate resident in L2 (fft_tma14.cuh);
@@ -1114,7 +1116,7 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         return GD_OK;
     }
     // any other length (Bluestein lines): gather to dense lines, transform, scatter back
-    long long chunk = (long long)((64ull << 20) / ((size_t)len * sizeof(cpx)));
+    long long chunk = (long long)(d.bluestein_chunk_bytes / 2 / ((size_t)len * sizeof(cpx)));
     if (chunk < 1) chunk = 1;
     if (chunk > nlines) chunk = nlines;
     cpx* buf;

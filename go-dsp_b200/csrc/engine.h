@@ -76,7 +76,7 @@ struct Device {
     static constexpr int AUX_STREAMS = 3;
     cudaStream_t stream_aux[AUX_STREAMS] = {nullptr};   // the other L2-sized chunks of a multi-pass transform (ForkJoin, engine.cu)
     cudaEvent_t ev_fork = nullptr, ev_pipe = nullptr, ev_join[AUX_STREAMS] = {nullptr};
-    cpx* wl[13] = {nullptr};             // intra-line tables exp(-2 pi i e/L), L = 2^k
+    cpx* wl[14] = {nullptr};             // intra-line tables exp(-2 pi i e/L), L = 2^k
     std::map<int, TwiddleTable> tw;      // keyed by log2 M
     std::map<long long, BluesteinPlan> blue;
     void* scratch[SCR_NSLOTS] = {nullptr};
@@ -110,6 +110,7 @@ struct Device {
     int huge_min_log2n = 22;             // plain forward / inverse transforms of at least 2^this points (one less in a batch) take the outer
                                          // four-step over the fused family (fft_pow2_huge): two sweeps at 0.30-0.37 of HBM, where the 4096-point
                                          // strided line passes of the two-launch schedule fall to 6-23 GS/s
+    int axis_single_max_log2 = 11;       // strided lines of up to 2^this points (any length on matrices narrower than 64 columns) are one pass
     int huge_l1 = 0;                     // measurement: log2 of the column length of that outer four-step (0 = the rule in fft_pow2_huge)
     int huge_sweeps = 0;                 // measurement / cross-check: 3 or 4 forces the three- / four-sweep formulation
     int tma_grid_cap = 0;                // fused size family: at most this many CTAs (0 = one per SM); leaves SMs to a concurrent kernel

@@ -178,15 +178,22 @@ __device__ __forceinline__ void line_transform(cpx (&x)[16], int p, cpx* __restr
         scatter_step<L, 16, 1>(x, p, sl);
         __syncthreads();
         gather_step<L>(x, p, sl);
-        if constexpr (SH::NSTEP == 3) {
+        if constexpr (SH::NSTEP >= 3) {
             __syncthreads();
             butterfly_step<L, 16, 16>(x, p, wl);
             scatter_step<L, 16, 16>(x, p, sl);
             __syncthreads();
             gather_step<L>(x, p, sl);
         }
+        if constexpr (SH::NSTEP == 4) {                   // L = 8192 (bluestein_small.cuh only): 16 x 16 x 16 x 2
+            __syncthreads();
+            butterfly_step<L, 16, 256>(x, p, wl);
+            scatter_step<L, 16, 256>(x, p, sl);
+            __syncthreads();
+            gather_step<L>(x, p, sl);
+        }
         __syncthreads();
-        butterfly_step<L, SH::LASTR, (SH::NSTEP == 2 ? 16 : 256)>(x, p, wl);
+        butterfly_step<L, SH::LASTR, (SH::NSTEP == 2 ? 16 : SH::NSTEP == 3 ? 256 : 4096)>(x, p, wl);
     }
 }
 

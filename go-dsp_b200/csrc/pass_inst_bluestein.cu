@@ -40,6 +40,7 @@ cudaError_t launch_bluestein_small(int log2la, const BluesteinSmallParams& a, in
         case 10: return launch_bs<10, 4>(a, num_sms, st);
         case 11: return launch_bs<11, 2>(a, num_sms, st);
         case 12: return launch_bs<12, 1>(a, num_sms, st);
+        case 13: return launch_bs<13, 1>(a, num_sms, st);      // 512 threads, the 8192-point sequence (139 KiB) in shared memory
     }
     return cudaErrorInvalidValue;
 }

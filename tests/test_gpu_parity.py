@@ -198,6 +198,31 @@ def test_bluestein_fused_small(gd, n):           # padded length <= 4096: one ke
     assert np.array_equal(gr, r2) and np.array_equal(gri, r2i)
 
 
+@pytest.mark.parametrize("n", [2049, 3000, 4095])
+def test_bluestein_fused_8192(gd, n):            # padded length 8192: still one kernel per transform (512 threads, 16 x 16 x 16 x 2)
+    godsp, capi, L = gd
+    assert L.gd_bluestein_padded_len(n) == 8192
+    b = 5
+    x = oracle.splitmix_complex(b * n, 12).reshape(b, n)
+    want = np.stack([oracle.fft(x[i]) for i in range(b)])
+    wanti = np.stack([oracle.ifft(x[i]) for i in range(b)])
+    got, goti = np.empty_like(x), np.empty_like(x)
+    capi.check(L.gd_fft_batch_c2c(x.ctypes.data, got.ctypes.data, n, b, 1))      # builds the plan (chirp, FFT(b)) as well
+    l0 = L.gd_kernel_launches()
+    capi.check(L.gd_fft_batch_c2c(x.ctypes.data, goti.ctypes.data, n, b, -1))
+    assert L.gd_kernel_launches() - l0 == 1
+    assert rel_l2(got, want) <= TOL and rel_l2(goti, wanti) <= TOL
+    r = oracle.fill_splitmix(n, 4)
+    assert rel_l2(godsp.fft.FFTReal(r), oracle.fft_real(r)) <= TOL and rel_l2(godsp.fft.IFFTReal(r), oracle.ifft_real(r)) <= TOL
+    capi.check(L.gd_set_option(b"bluestein_fused", 0))      # against the two-transform path (different arithmetic: not bit-equal)
+    try:
+        g2 = np.empty_like(x)
+        capi.check(L.gd_fft_batch_c2c(x.ctypes.data, g2.ctypes.data, n, b, 1))
+    finally:
+        capi.check(L.gd_set_option(b"bluestein_fused", 1))
+    assert rel_l2(got, g2) <= 1e-13
+
+
 def test_real_roundtrips(gd):                    # C2: IFFT(FFTReal(x)) ~ x and FFT(IFFTReal(x)) ~ x
     godsp = gd[0]
     for n in (4096, 1000003, 1 << 16):
