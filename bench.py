@@ -561,8 +561,10 @@ def run_ours(args):
 
 
 def run_fft_sizes(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
-    """Batched transforms of the other power-of-two sizes with a fused kernel (2^13 .. 2^18, fft_tma14.cuh): 2^28 points per
-    GPU and call, device resident (inputs larger than L2); one row of every size against the oracle."""
+    """Batched transforms of the other sizes: the fused size family (2^13 .. 2^19, fft_tma14.cuh), the outer four-step over it
+    (2^21 .. 2^24: two sweeps) and Bluestein lengths (one kernel per transform up to a padded length of 8192, streaming kernels
+    around plain transforms above). 2^28 points per GPU and call, device resident (inputs larger than L2); one transform of
+    every size against the oracle."""
     from godsp import _capi as capi
     import oracle
     total = 1 << 28
@@ -571,21 +573,23 @@ def run_fft_sizes(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
     capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), total * 2, 11, (rank * total) * 2, sp))
     torch.cuda.synchronize()
     rows, worst, launches = {}, 0.0, 0
-    for lg in range(13, 19):
-        n = 1 << lg
+    sizes = [("2^%d" % lg, 1 << lg) for lg in range(13, 25) if lg != 20] + [("%d" % n, n) for n in (1000, 4095, 30000, 1000003)]
+    for name, n in sizes:
         b = total // n
         ms, nl, _ = timed(lambda: capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, b, 1, sp)), 3, 3)
         launches += nl
         r = b - 1                                            # the last transform of the batch against the oracle
-        xin = x.view(b, 2 * n)[r].cpu().numpy().view(np.complex128)
-        got = y.view(b, 2 * n)[r].cpu().numpy().view(np.complex128)
+        xin = x[: 2 * n * b].view(b, 2 * n)[r].cpu().numpy().view(np.complex128)
+        got = y[: 2 * n * b].view(b, 2 * n)[r].cpu().numpy().view(np.complex128)
         err = rel_l2(got, oracle.fft(np.ascontiguousarray(xin)))
         worst = max(worst, err)
-        rows["2^%d" % lg] = {"gs_per_gpu": n * b / (ms * 1e-3) / 1e9, "ms": ms, "hbm_frac": 32.0 * n * b / (ms * 1e-3) / 1e9 / hbm_peak}
+        rows[name] = {"gs_per_gpu": n * b / (ms * 1e-3) / 1e9, "ms": ms, "hbm_frac": 32.0 * n * b / (ms * 1e-3) / 1e9 / hbm_peak}
     del x, y
     torch.cuda.empty_cache()
     return {"metric": "FFT GS/s per GPU (complex128, batched, 2^28 points per call) by transform size", "sizes": rows,
-            "kernel": "gd::fft_tma14_kernel<LA, LB, ROWS> (both four-step passes in one persistent TMA-fed launch, N = LA x LB)",
+            "kernel": "2^13 .. 2^19: gd::fft_tma14_kernel<LA, LB, ROWS> (both four-step passes in one persistent TMA-fed launch, N = LA x LB); "
+                      "2^21 .. 2^24: the same kernel on columns with the outer twiddle on its stores + one row pass with the transposed store; "
+                      "other lengths: Bluestein (hbm_frac at 32 B per point of the unpadded length)",
             "_parity": {"max_rel_l2": allmax(torch, dist, world, worst), "vs": "oracle.fft on the last transform of every batch, every rank"},
             "_launches": int(launches)}
 
