@@ -118,7 +118,8 @@ Status fft_tma_2p20(Device& d, const cpx* in, long long in_dist, cpx* out, long 
         cudaError_t e = cudaMemsetAsync(cnt, 0, (2 * (size_t)CH + 2) * sizeof(int), st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(counters)"); break; }
         const long long nitems = 2 * nb * (TMA_L / TMA_T);
-        const int grid = (int)(nitems < d.num_sms ? nitems : d.num_sms);
+        const int sms = d.tma_grid_cap > 0 && d.tma_grid_cap < d.num_sms ? d.tma_grid_cap : d.num_sms;
+        const int grid = (int)(nitems < sms ? nitems : sms);
         if (prof) e = inv ? launch_one<true, true>(grid, m_x, m_int, m_out, f, st) : launch_one<false, true>(grid, m_x, m_int, m_out, f, st);
         else e = inv ? launch_one<true, false>(grid, m_x, m_int, m_out, f, st) : launch_one<false, false>(grid, m_x, m_int, m_out, f, st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "fft_tma_fused_kernel launch"); break; }

@@ -16,7 +16,7 @@ while args and args[0].startswith("--"):
     if k == "--batch": batch = v
     if k == "--iters": iters = v
 L = capi.lib(); capi.check(L.gd_use_device(0))
-DEFAULTS = {"tma": 1, "tma_delay": 2, "tma_slots": 3, "tma_opt": 0, "tma_prof": 0}
+DEFAULTS = {"tma": 1, "tma_delay": 2, "tma_slots": 3, "tma_opt": 0, "tma_prof": 0, "tma_grid_cap": 0}
 n = 1 << 20
 x = torch.empty(batch * n * 2, dtype=torch.float64, device="cuda")
 y = torch.empty_like(x)
@@ -49,7 +49,8 @@ for combo in (args or [""]):
             ts.append(e0.elapsed_time(e1))
     ey = (y.view(batch, -1) ** 2).sum(1)
     bad = int((((ey / n - ex).abs() / ex) > 1e-12).sum())
-    out = {"opts": combo, "batch": batch, "gs_best": batch * n / min(ts) / 1e6, "gs_median": batch * n / float(np.median(ts)) / 1e6, "bad_rows": bad}
+    out = {"opts": combo, "batch": batch, "gs_best": batch * n / min(ts) / 1e6, "gs_median": batch * n / float(np.median(ts)) / 1e6,
+           "gs_last_third": batch * n / float(np.mean(ts[-max(1, len(ts) // 3):])) / 1e6, "bad_rows": bad}
     if prof:
         buf = np.zeros(148 * 32, np.int64)
         nc = L.gd_tma_profile_read(buf.ctypes.data, 148)
