@@ -26,14 +26,12 @@ int pass32_tile_lines(int variant);
                                    int st_conj, double scale);                                                                           \
     bool tma##LG##_cols_applicable(const cpx* src, const cpx* dst, long long len, long long ncols, long long pitch);                     \
     Status fft_tma_2p##LG(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, \
-                          double scale, cudaStream_t st, int tw2_log2m, long long tw2_col0, long long nmat, long long in_mdist,         \
-                          long long out_mdist);
+                          double scale, cudaStream_t st, const Tma2dExtra& ex);
 GD_TMA2D_DECL(13) GD_TMA2D_DECL(14) GD_TMA2D_DECL(15) GD_TMA2D_DECL(16) GD_TMA2D_DECL(17) GD_TMA2D_DECL(18) GD_TMA2D_DECL(19)
 struct Tma2dEntry {
     bool (*rows_ok)(const void*, long long, const cpx*, long long, long long, int, int, double);
     bool (*cols_ok)(const cpx*, const cpx*, long long, long long, long long);
-    Status (*run)(Device&, int, const cpx*, long long, cpx*, long long, long long, bool, double, cudaStream_t, int, long long, long long, long long,
-                  long long);
+    Status (*run)(Device&, int, const cpx*, long long, cpx*, long long, long long, bool, double, cudaStream_t, const Tma2dExtra&);
     int unit;                                            // transforms / columns per phase: 2^20 / N
 };
 static const Tma2dEntry* tma2d_entry(const Device& d, int log2n) {
@@ -296,6 +294,11 @@ Status transpose_batched(const cpx* in, cpx* out, long long batch, long long row
 //  three sweeps (beyond): (1) as above, (2) one transpose to [N2][N1], (3) columns of length N2 in place: out[k2][k1] = X[k1 + N1 k2].
 //  four sweeps (huge_sweeps = 4, the first formulation: columns, twiddle kernel, rows, transpose) stay as the cross-check.
 // Forward and inverse (every sub-step inverted, conjugate twiddle) only; needs a second N-element buffer.
+static Tma2dExtra huge_extra(int log2n, long long nmat, long long in_mdist, long long out_mdist) {
+    Tma2dExtra ex;
+    ex.tw2_log2m = log2n; ex.nmat = nmat; ex.in_mdist = in_mdist; ex.out_mdist = out_mdist;
+    return ex;
+}
 static Status fft_pow2_huge(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, int log2n, long long batch,
                             const FusedOps& ops, cudaStream_t st) {
     const bool fwd = ops.ld_flags == 0 && ops.st_flags == 0;
@@ -329,7 +332,7 @@ static Status fft_pow2_huge(Device& d, const void* in, long long in_dist, cpx* o
     if (per > 1 && te->cols_ok((const cpx*)in, tmp, N1, N2, N2)) {
         for (long long b0 = 0; b0 < batch; b0 += per) {
             const long long nb = batch - b0 < per ? batch - b0 : per;
-            GD_TRY(te->run(d, 1, (const cpx*)in + b0 * in_dist, N2, tmp, N2, N2, inv, inv ? 1.0 / (double)N1 : 1.0, st, log2n, 0, nb, in_dist, N));
+            GD_TRY(te->run(d, 1, (const cpx*)in + b0 * in_dist, N2, tmp, N2, N2, inv, inv ? 1.0 / (double)N1 : 1.0, st, huge_extra(log2n, nb, in_dist, N)));
             PassParams r = base_params(d, l2);
             r.in = tmp; r.out = out + b0 * out_dist;
             r.nlines = nb * N1; r.inner = N1;
@@ -346,7 +349,7 @@ static Status fft_pow2_huge(Device& d, const void* in, long long in_dist, cpx* o
         cpx* dst = out + b * out_dist;
         if (te && te->cols_ok(src, tmp, N1, N2, N2)) {
             cpx* mid = three ? dst : tmp;                                        // three sweeps: columns -> dst, transpose -> tmp, columns -> dst
-            GD_TRY(te->run(d, 1, src, N2, mid, N2, N2, inv, inv ? 1.0 / (double)N1 : 1.0, st, log2n, 0, 1, 0, 0));   // (1) columns n2, twiddle on store
+            GD_TRY(te->run(d, 1, src, N2, mid, N2, N2, inv, inv ? 1.0 / (double)N1 : 1.0, st, huge_extra(log2n, 1, 0, 0)));   // (1) columns n2, twiddle on store
             if (three) {
                 GD_TRY(transpose_batched(mid, tmp, 1, N1, N2, st));              // (2) [N1][N2] -> [N2][N1]
                 GD_TRY(fft_axis(d, tmp, dst, 1, N2, N1, dir, st));               // (3) lines over n2 at stride N1
@@ -404,7 +407,7 @@ Status fft_pow2(Device& d, const void* in, long long in_dist, cpx* out, long lon
         const double scl = (ops.st_flags & ST_SCALE) ? ops.scale : 1.0;
         const long long main = batch - batch % te->unit;
         if (main > 0 && te->rows_ok(in, in_dist, out, out_dist, main, lc, sc, scl)) {
-            GD_TRY(te->run(d, 0, (const cpx*)in, in_dist, out, out_dist, main, lc != 0, scl, st, 0, 0, 1, 0, 0));
+            GD_TRY(te->run(d, 0, (const cpx*)in, in_dist, out, out_dist, main, lc != 0, scl, st, Tma2dExtra()));
             if (main == batch) return GD_OK;
             return fft_pow2(d, (const cpx*)in + main * in_dist, in_dist, out + main * out_dist, out_dist, log2n, batch - main, ops, st);
         }
@@ -814,6 +817,43 @@ Status fourstep_lines_exchange(Device& d, const cpx* slab, cpx* tmp, cpx* const*
     return GD_OK;
 }
 
+// The sharded four-step with the exchange fused into the first line pass (TW2 = 2 in fft_tma14.cuh): the length-n1 lines of this
+// rank's [n1][w] slab run through the fused family in column mode, the outputs leave multiplied by w_N^(k1 n2), and the TMA stores
+// of pass 2 go straight into the ranks' receive buffers over NVLink: row k1 of the slab is row k1 % K of block `rank` ([K][w],
+// K = n1 / world) of rank k1 / K. No intermediate slab, no exchange kernel, NVLink busy while the butterflies run.
+bool fourstep_fused_supported(Device& d, long long n1, long long n2, int world) {
+    if (world < 1 || world > 8 || !is_pow2(n1) || !is_pow2(n2) || n1 % world || n2 % world) return false;
+    const int l1 = ilog2ll(n1), l2 = ilog2ll(n2);
+    if (l1 < 13 || l1 > 17 || l2 < 13 || l2 > 18 || !tma2d_entry(d, l1) || !tma2d_entry(d, l2)) return false;
+    const long long w = n2 / world, k = n1 / world;
+    const int lb1 = 1 << (l1 / 2), la2 = 1 << ((l2 + 1) / 2);                 // LB of the n1 lines, LA of the n2 lines
+    return w % tma2d_entry(d, l1)->unit == 0 && k % tma2d_entry(d, l2)->unit == 0 && lb1 % world == 0 &&
+           (world == 1 || (la2 % world == 0 && world % 2 == 0)) && w < (1LL << 30);
+}
+Status fourstep_lines_peer(Device& d, const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,
+                           cudaStream_t st) {
+    if (!slab || !peer_recv || rank < 0 || rank >= world || !fourstep_fused_supported(d, n1, (1LL << log2n) / n1, world) || w * world * n1 != (1LL << log2n))
+        return invalid("fourstep_lines_peer: unsupported shape (see gd_fourstep_fused_supported)");
+    const Tma2dEntry* te = tma2d_entry(d, ilog2ll(n1));
+    if (!te->cols_ok(slab, slab, n1, w, w)) return invalid("fourstep_lines_peer: slab alignment");
+    Tma2dExtra ex;
+    ex.tw2_log2m = log2n; ex.tw2_col0 = (long long)rank * w;
+    ex.npeer = world; ex.peer = peer_recv; ex.peer_off = (long long)rank * (n1 / world) * w;
+    return te->run(d, 1, slab, w, const_cast<cpx*>(slab), w, w, false, 1.0, st, ex);
+}
+// Second half: this rank's receive buffer [world][K][w] -- row k1 of the spectrum's [n1][n2] view in `world` segments of w = n2 / world
+// points -- through the fused family in row mode on segmented lines: out[k1 local][k2] = X[k1 + n1 k2], K transforms of n2 points.
+Status fourstep_rows_seg(Device& d, const cpx* recv, cpx* out, long long n2, long long k, int world, cudaStream_t st) {
+    if (!recv || !out || recv == out || world < 1 || n2 % world) return invalid("fourstep_rows_seg: bad arguments");
+    const long long w = n2 / world;
+    if (world == 1) { FusedOps none; return fft_pow2(d, recv, n2, out, n2, ilog2ll(n2), k, none, st); }
+    const Tma2dEntry* te = is_pow2(n2) ? tma2d_entry(d, ilog2ll(n2)) : nullptr;
+    if (!te || k % te->unit || ((uintptr_t)recv % 16) || ((uintptr_t)out % 16)) return invalid("fourstep_rows_seg: unsupported shape (see gd_fourstep_fused_supported)");
+    Tma2dExtra ex;
+    ex.seg = world; ex.seg_dist = k * w;
+    return te->run(d, 0, recv, w, out, n2, k, false, 1.0, st, ex);
+}
+
 // FFT2 on row blocks: both exchanges are strided block copies into peer memory (no repack kernels, no NCCL data
 // movement). For every peer h: dst_h[dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c], r < rows, c < cols.
 __global__ void __launch_bounds__(256) peer_block_copy_kernel(const cpx* __restrict__ src, const __grid_constant__ PeerPtrs peers, long long rows, long long cols,
@@ -1118,7 +1158,7 @@ static Status fft_axis(Device& d, const cpx* src, cpx* dst, long long outer, lon
         const long long main = ctotal - ctotal % te->unit;
         if (main > 0 && te->cols_ok(src + cfirst, dst + cfirst, len, main, s)) {
             for (long long o = 0; o < outer; o++)
-                GD_TRY(te->run(d, 1, src + o * len * s + cfirst, s, dst + o * len * s + cfirst, s, main, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st, 0, 0, 1, 0, 0));
+                GD_TRY(te->run(d, 1, src + o * len * s + cfirst, s, dst + o * len * s + cfirst, s, main, dir < 0, dir < 0 ? 1.0 / (double)len : 1.0, st, Tma2dExtra()));
             if (main == ctotal) return GD_OK;
             col0 = cfirst + main; ncols = ctotal - main;            // the remainder: fewer columns than a phase, two-launch path below
         }

@@ -179,6 +179,20 @@ Status convolve_linear(Device& d, const cpx* x, long long nx, const cpx* h, long
 Status pwelch_finalize(const double* raw, long long lp, long long nsegs, double norm, double* pxx, cudaStream_t st);
 
 // ---- distributed four-step (C5) building blocks -------------------------------------------
+// optional operators of a fused-family launch (tma14_host.cuh)
+struct Tma2dExtra {
+    int tw2_log2m = 0;               // COLS: outputs leave multiplied by w_M^((tw2_col0 + column) k), M = 2^tw2_log2m
+    long long tw2_col0 = 0;
+    long long nmat = 1, in_mdist = 0, out_mdist = 0;   // COLS: the same columns of nmat matrices in the same launches
+    int npeer = 0;                   // COLS + tw2: rows of the output spread over npeer ranks' buffers (peer[h] + peer_off, row pitch out_dist)
+    cpx* const* peer = nullptr;
+    long long peer_off = 0;
+    int seg = 0;                     // ROWS: a transform is seg segments, seg_dist elements apart
+    long long seg_dist = 0;
+};
+bool fourstep_fused_supported(Device& d, long long n1, long long n2, int world);
+Status fourstep_lines_peer(Device& d, const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n, cudaStream_t st);
+Status fourstep_rows_seg(Device& d, const cpx* recv, cpx* out, long long n2, long long k, int world, cudaStream_t st);
 Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st, int dir = 1);
 Status repack_gkw(const cpx* in, cpx* out, long long G, long long K, long long W, cudaStream_t st);
 Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,

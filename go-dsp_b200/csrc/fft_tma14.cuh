@@ -24,6 +24,7 @@
 // TW2 (COLS only): the lines are the length-N1 columns of ONE transform of M = N1 x N2 points laid out as [N1][N2]; output k1 of
 // column n2 leaves multiplied by w_M^(n2 k1), so the outer four-step's twiddle sweep disappears (fft_pow2_huge in engine.cu).
 // The three bases per thread and tile come from sincospi of exactly reduced exponents (no table above 2^24 entries).
+// TW2 = 2: the same, and the stores go to the ranks of a sharded transform (T14Peers below).
 #pragma once
 #include <type_traits>
 #include "fft_tma.cuh"
@@ -73,7 +74,13 @@ struct Tma14Params {
     int tw2_log2m;               // TW2 (COLS): the stores of pass 2 carry an outer four-step twiddle w_M^(column * k), M = 2^tw2_log2m,
     long long tw2_col0;          //   column = tw2_col0 + the column's index in this launch, k = the output index in the line
     int bshift;                  // COLS: a launch over several matrices (dimension 3 of the maps) has 2^bshift phases per matrix; 31 = one matrix
+    int npeer;                   // TW2 == 2: number of ranks G the rows of the output are spread over (T14Peers)
+    int seg;                     // ROWS, > 0: a transform's LA rows of LB points are `seg` segments of LA / seg rows (dimension 2 of the input map)
 };
+// TW2 == 2 (COLS): the output rows k = k1 + LA k2 of the slab belong to rank k / (N / G): instead of one local output map the stores of
+// pass 2 go through one map per rank, straight into that rank's receive buffer over NVLink (a half tile = max(1, G / 2) boxes of
+// LB / G rows of k2). The sharded four-step's exchange is then the store phase of its first line pass.
+struct T14Peers { CUtensorMap m[8]; };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned long long* bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
@@ -103,10 +110,11 @@ __device__ __forceinline__ void t14_coords(int type, int grp, int c, int h, int 
     }
 }
 
-template <int LA, int LB, int MODE, bool INV, bool PROF, bool TW2 = false>
+template <int LA, int LB, int MODE, bool INV, bool PROF, int TW2 = 0>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_int,
-                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ Tma14Params a) {
+                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ Tma14Params a,
+                 const __grid_constant__ std::conditional_t<TW2 == 2, T14Peers, int> peers) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     cpx* land = reinterpret_cast<cpx*>(smem_raw);
     cpx* work = reinterpret_cast<cpx*>(smem_raw + TMA_NSLOT * T14_HALF_BYTES);
@@ -173,6 +181,7 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     mbar_expect_tx(fb, T14_HALF_BYTES);
                     int c0, c1, c2, c3;
                     t14_coords<LA, LB, MODE>(w.type, w.tf, w.c, h, S, a.bshift, c0, c1, c2, c3, true);
+                    if (MODE == T14_ROWS && a.seg > 0 && w.type == 0) { c3 = c2; c1 = 0; c2 = (a.seg / 2) * h; }   // rows (segment, row in segment)
                     if constexpr (LA == 1024) {
                         // a box has at most 256 rows: the 512 rows of a pass-1 half arrive as two copies on the same barrier
                         if (w.type == 0) {
@@ -214,12 +223,27 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 const cpx* srcb = work + (size_t)g * T14_WELEMS;
                 if (pi.type == 1) {
                     int c0, c1, c2, c3;
-                    t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, 0, S, a.bshift, c0, c1, c2, c3, false);
-                    tma_store_4d(&tm_out, c0, c1, c2, c3, srcb);
-                    tma_commit();
-                    t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, 1, S, a.bshift, c0, c1, c2, c3, false);
-                    tma_store_4d(&tm_out, c0, c1, c2, c3, srcb + HALF_ELEMS);
-                    tma_commit();
+                    if constexpr (TW2 == 2) {
+                        // rows k2 of the tile go to rank k2 / (LB / G), local row k2 % (LB / G): boxes of min(LB / 2, LB / G) rows
+                        const int G = a.npeer, per = LB / G, rows = per < LB / 2 ? per : LB / 2, nbox = (LB / 2) / rows;
+#pragma unroll 1
+                        for (int hf = 0; hf < 2; hf++) {
+                            t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, hf, S, a.bshift, c0, c1, c2, c3, false);
+#pragma unroll 1
+                            for (int jb = 0; jb < nbox; jb++) {
+                                const int k2 = c2 + jb * rows;
+                                tma_store_4d(&peers.m[k2 / per], c0, c1, k2 % per, c3, srcb + (size_t)hf * HALF_ELEMS + (size_t)jb * rows * (4096 / LB));
+                            }
+                            tma_commit();
+                        }
+                    } else {
+                        t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, 0, S, a.bshift, c0, c1, c2, c3, false);
+                        tma_store_4d(&tm_out, c0, c1, c2, c3, srcb);
+                        tma_commit();
+                        t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, 1, S, a.bshift, c0, c1, c2, c3, false);
+                        tma_store_4d(&tm_out, c0, c1, c2, c3, srcb + HALF_ELEMS);
+                        tma_commit();
+                    }
                 } else {
                     // the slot is free once pass 2 of the phase that used it is complete (polling earlier, while the tile is
                     // still being computed, was slower: cols 2.14 -> 2.48 ms)
@@ -337,7 +361,7 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             tb32 = cmul(__ldg(a.tw_hi + (e32 >> 12)), __ldg(a.tw_lo + (e32 & 4095u)));
             if (INV) tb0 = make_double2(tb0.x * a.scale, tb0.y * a.scale);
         }
-        if constexpr (TW2 && MODE == T14_COLS) {
+        if constexpr (TW2 != 0 && MODE == T14_COLS) {
             if (wi.type == 1) {
                 // outer twiddle of this line's outputs k = k1 + LA k2, k2 = KB j' + k_lo + 32 m: w^(col (k1 + LA KB j')), w^(col LA), w^(32 col LA)
                 const unsigned long long mask = (1ULL << a.tw2_log2m) - 1ULL;
@@ -403,7 +427,7 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     for (int m = 0; m < NJ; m++) s[(kl + 32 * m) * LINES] = x[NJ * kl + m];
             }
         } else {
-            if constexpr (TW2 && MODE == T14_COLS) {
+            if constexpr (TW2 != 0 && MODE == T14_COLS) {
                 cpx c[KB];
                 c[0] = tb0;
 #pragma unroll

@@ -55,11 +55,13 @@ static bool tma2d_cols_applicable(const cpx* src, const cpx* dst, long long len,
            ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
 }
 
-template <int LA, int LB, int MODE, bool INV, bool PROF = false, bool TW2 = false>
-static cudaError_t launch14(int grid, const CUtensorMap& mx, const CUtensorMap& mi, const CUtensorMap& mo, const Tma14Params& f, cudaStream_t st) {
+template <int LA, int LB, int MODE, bool INV, bool PROF = false, int TW2 = 0>
+static cudaError_t launch14(int grid, const CUtensorMap& mx, const CUtensorMap& mi, const CUtensorMap& mo, const Tma14Params& f, cudaStream_t st,
+                            const T14Peers* peers = nullptr) {
     cudaError_t e = cudaFuncSetAttribute(fft_tma14_kernel<LA, LB, MODE, INV, PROF, TW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T14_SMEM);   // per device
     if (e != cudaSuccess) return e;
-    fft_tma14_kernel<LA, LB, MODE, INV, PROF, TW2><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f);
+    if constexpr (TW2 == 2) fft_tma14_kernel<LA, LB, MODE, INV, PROF, TW2><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f, *peers);
+    else fft_tma14_kernel<LA, LB, MODE, INV, PROF, TW2><<<grid, TMA_THREADS, T14_SMEM, st>>>(mx, mi, mo, f, 0);
     return cudaGetLastError();
 }
 
@@ -71,9 +73,17 @@ static inline cuuint64_t clamp_stride(unsigned long long v) { return v < (1ULL <
 //            w_M^((tw2_col0 + c) k), M = 2^tw2_log2m (conjugated for inv): the twiddle of an outer four-step over these lines.
 //            nmat > 1: the same columns of nmat matrices (matrix m at in + m * in_mdist / out + m * out_mdist) in the same launches;
 //            count / UNIT must be a power of two <= 512 (the matrices ride on dimension 3 of the tensor maps).
+//            ex.npeer = G > 0 (with tw2_log2m): output row k of the slab goes to rank h = k / (N / G), row k % (N / G) of the matrix with
+//            row pitch out_dist at ex.peer[h] + ex.peer_off: the stores of pass 2 are the exchange of the sharded four-step.
+// mode ROWS, ex.seg = G > 1: transform t is G segments of N / G contiguous points, segment g at in + g * ex.seg_dist + t * in_dist.
 template <int LA, int LB>
 static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, double scale,
-                         cudaStream_t st, int tw2_log2m, long long tw2_col0, long long nmat, long long in_mdist, long long out_mdist) {
+                         cudaStream_t st, const Tma2dExtra& ex) {
+    const int tw2_log2m = ex.tw2_log2m;
+    const long long tw2_col0 = ex.tw2_col0, in_mdist = ex.in_mdist, out_mdist = ex.out_mdist;
+    long long nmat = ex.nmat;
+    if (ex.npeer && (mode != T14_COLS || !tw2_log2m || ex.npeer > 8 || (int)LB % ex.npeer || !ex.peer || nmat > 1)) return invalid14("fused kernel: bad peer-store launch");
+    if (ex.seg > 1 && (mode != T14_ROWS || LA > 512 || (int)LA % ex.seg || (ex.seg & 1))) return invalid14("fused kernel: bad segmented-row launch");
     using SH = T14Shape<LA, LB>;
     constexpr cuuint64_t A = LA, Bq = LB, N = SH::N, LNA = SH::LINES_A, LNB = SH::LINES_B, UNIT = SH::UNIT;
     TmaEncodeFn14 enc;
@@ -147,12 +157,24 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         const cuuint64_t nm = multi ? (cuuint64_t)(ng / gpm) : 1;      // matrices of this launch (CH is a multiple of gpm)
         const cuuint64_t nt = multi ? (cuuint64_t)count : (cuuint64_t)ng * UNIT;   // transforms / columns (per matrix) of this launch
         CUtensorMap m_x, m_out;
+        T14Peers peer_maps;
         if (mode == T14_ROWS) {
-            const cuuint64_t dx[4] = {2 * Bq, A, nt, 1}, dout[4] = {2 * A, Bq, nt, 1};
-            const cuuint32_t bx[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)(A / 2 > 256 ? 256 : A / 2), 1, 1}, bo[4] = {(cuuint32_t)(2 * LNB), (cuuint32_t)(Bq / 2), 1, 1};
-            const cuuint64_t sx[3] = {Bq * 16, (cuuint64_t)in_dist * 16, clamp_stride((cuuint64_t)in_dist * 16 * nt)};
+            const cuuint64_t dout[4] = {2 * A, Bq, nt, 1};
+            const cuuint32_t bo[4] = {(cuuint32_t)(2 * LNB), (cuuint32_t)(Bq / 2), 1, 1};
             const cuuint64_t so[3] = {A * 16, (cuuint64_t)out_dist * 16, clamp_stride((cuuint64_t)out_dist * 16 * nt)};
-            if ((rc = map4(enc, in + g0 * (long long)UNIT * in_dist, dx, sx, bx, &m_x)) != GD_OK) break;
+            if (ex.seg > 1) {
+                // rows n1 = g * (LA / G) + r of transform t: (r, g, t) are dimensions 1, 2, 3; half a tile is G / 2 segments
+                const cuuint64_t sg = (cuuint64_t)ex.seg;
+                const cuuint64_t dx[4] = {2 * Bq, A / sg, sg, nt};
+                const cuuint32_t bx[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)(A / sg), (cuuint32_t)(sg / 2), 1};
+                const cuuint64_t sx[3] = {Bq * 16, (cuuint64_t)ex.seg_dist * 16, (cuuint64_t)in_dist * 16};
+                if ((rc = map4(enc, in + g0 * (long long)UNIT * in_dist, dx, sx, bx, &m_x)) != GD_OK) break;
+            } else {
+                const cuuint64_t dx[4] = {2 * Bq, A, nt, 1};
+                const cuuint32_t bx[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)(A / 2 > 256 ? 256 : A / 2), 1, 1};
+                const cuuint64_t sx[3] = {Bq * 16, (cuuint64_t)in_dist * 16, clamp_stride((cuuint64_t)in_dist * 16 * nt)};
+                if ((rc = map4(enc, in + g0 * (long long)UNIT * in_dist, dx, sx, bx, &m_x)) != GD_OK) break;
+            }
             if ((rc = map4(enc, out + g0 * (long long)UNIT * out_dist, dout, so, bo, &m_out)) != GD_OK) break;
         } else {
             const cuuint64_t pi_ = (cuuint64_t)in_dist * 16, po = (cuuint64_t)out_dist * 16;
@@ -161,13 +183,22 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
             const cuuint64_t sx[3] = {pi_, pi_ * Bq, multi ? (cuuint64_t)in_mdist * 16 : clamp_stride(pi_ * N)};
             const cuuint64_t so[3] = {po, po * A, multi ? (cuuint64_t)out_mdist * 16 : clamp_stride(po * N)};
             if ((rc = map4(enc, multi ? in + m0 * in_mdist : in + g0 * (long long)UNIT, dx, sx, bx, &m_x)) != GD_OK) break;
-            if ((rc = map4(enc, multi ? out + m0 * out_mdist : out + g0 * (long long)UNIT, dout, so, bo, &m_out)) != GD_OK) break;
+            if (ex.npeer) {
+                // one output map per rank: its LB / G rows of k2 (N / G rows of the slab), the same columns
+                const cuuint64_t per = Bq / (cuuint64_t)ex.npeer;
+                const cuuint64_t dp[4] = {2 * nt, A, per, 1};
+                const cuuint32_t bp[4] = {(cuuint32_t)(2 * LNA), (cuuint32_t)SH::RA, (cuuint32_t)(per < Bq / 2 ? per : Bq / 2), 1};
+                const cuuint64_t sp[3] = {po, po * A, clamp_stride(po * A * per)};
+                for (int h = 0; h < ex.npeer && rc == GD_OK; h++) rc = map4(enc, ex.peer[h] + ex.peer_off + g0 * (long long)UNIT, dp, sp, bp, &peer_maps.m[h]);
+                if (rc != GD_OK) break;
+                m_out = peer_maps.m[0];
+            } else if ((rc = map4(enc, multi ? out + m0 * out_mdist : out + g0 * (long long)UNIT, dout, so, bo, &m_out)) != GD_OK) break;
         }
         f.batch = (int)ng; f.delay = D; f.nslots = S; f.scratch = scratch;
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.scale = scale;
         f.tw2_log2m = tw2_log2m; f.tw2_col0 = multi ? tw2_col0 : tw2_col0 + g0 * (long long)UNIT;
-        f.bshift = bshift;
+        f.bshift = bshift; f.npeer = ex.npeer; f.seg = ex.seg > 1 ? ex.seg : 0;
         f.prof = nullptr;
         if (d.tma_prof) {
             long long* pr;
@@ -181,7 +212,8 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         const int sms = d.tma_grid_cap > 0 && d.tma_grid_cap < d.num_sms ? d.tma_grid_cap : d.num_sms;
         const int grid = (int)(nitems < sms ? nitems : sms);
         if constexpr (LB <= 256) {
-            if (tw2_log2m) e = inv ? launch14<LA, LB, T14_COLS, true, false, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, false, true>(grid, m_x, m_int, m_out, f, st);
+            if (tw2_log2m && ex.npeer) e = inv ? launch14<LA, LB, T14_COLS, true, false, 2>(grid, m_x, m_int, m_out, f, st, &peer_maps) : launch14<LA, LB, T14_COLS, false, false, 2>(grid, m_x, m_int, m_out, f, st, &peer_maps);
+            else if (tw2_log2m) e = inv ? launch14<LA, LB, T14_COLS, true, false, 1>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, false, 1>(grid, m_x, m_int, m_out, f, st);
             else if (f.prof && !inv && LA == LB) e = mode == T14_ROWS ? launch14<LA, LB, T14_ROWS, false, LA == LB>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, LA == LB>(grid, m_x, m_int, m_out, f, st);
             else if (mode == T14_ROWS) e = inv ? launch14<LA, LB, T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
             else e = inv ? launch14<LA, LB, T14_COLS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false>(grid, m_x, m_int, m_out, f, st);
@@ -209,10 +241,8 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         return tma2d_cols_applicable<LA, LB>(src, dst, len, ncols, pitch);                                                              \
     }                                                                                                                                   \
     Status fft_tma_2p##LG(Device& d, int mode, const cpx* in, long long in_dist, cpx* out, long long out_dist, long long count, bool inv, \
-                          double scale, cudaStream_t st, int tw2_log2m, long long tw2_col0, long long nmat, long long in_mdist,         \
-                          long long out_mdist) {                                                                                        \
-        return fft_tma_2d<LA, LB>(d, mode, in, in_dist, out, out_dist, count, inv, scale, st, tw2_log2m, tw2_col0, nmat, in_mdist,      \
-                                  out_mdist);                                                                                           \
+                          double scale, cudaStream_t st, const Tma2dExtra& ex) {                                                        \
+        return fft_tma_2d<LA, LB>(d, mode, in, in_dist, out, out_dist, count, inv, scale, st, ex);                                      \
     }
 
 }  // namespace gd

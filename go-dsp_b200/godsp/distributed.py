@@ -130,6 +130,19 @@ class PeerExchange:
         _capi.check(self.L.gd_fourstep_lines_exchange_dev(slab.data_ptr(), tmp.data_ptr(), self.ptr_array, n1, w, self.rank, self.world, log2n,
                                                           self.ops._sp()))
 
+    def fused_supported(self, n1, n2):
+        """both line lengths are in the range of the fused TMA kernel for this world size (gd_fourstep_fused_supported)"""
+        return self.L.gd_fourstep_fused_supported(n1, n2, self.world) == 1
+
+    def lines_peer(self, slab, n1, w, log2n):
+        """length-n1 lines of the slab, outer twiddle, and the exchange as the kernel's own TMA stores into every rank's
+        receive buffer over NVLink: receive buffers become [world][K][w] (gd_fourstep_lines_peer_dev)"""
+        _capi.check(self.L.gd_fourstep_lines_peer_dev(slab.data_ptr(), self.ptr_array, n1, w, self.rank, self.world, log2n, self.ops._sp()))
+
+    def rows_seg(self, out, n2, k):
+        """the K rows of the receive buffer (n2 points each, in `world` segments) -> out[K][n2] (gd_fourstep_rows_seg_dev)"""
+        _capi.check(self.L.gd_fourstep_rows_seg_dev(self.recv.data_ptr(), out.data_ptr(), n2, k, self.world, self.ops._sp()))
+
     def block_copy(self, src, rows, cols, src_step, src_pitch, dst_off, dst_pitch):
         """every peer h: peer_buffer[h][dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c]"""
         _capi.check(self.L.gd_peer_block_copy_dev(src.data_ptr(), self.ptr_array, self.world, self.rank, rows, cols, src_step, src_pitch,
@@ -164,16 +177,26 @@ def split_1d(n, world):
     return n1, n2, n1 // world, n2 // world
 
 
-def fft_1d_sharded(slab, n, ops, group=None, work=None, peer=None):
+def fft_1d_sharded(slab, n, ops, group=None, work=None, peer=None, fused=False):
     """Forward transform of one n-point signal.  `slab`: this rank's [N1][W] column slab (flattened; overwritten by the
-    NCCL formulation, preserved by the peer-memory one).
+    NCCL formulation, preserved by the peer-memory ones).
     Returns this rank's [N2][K] slab of the spectrum (a new tensor, or `work` if given: n/world elements).
     peer: a PeerExchange of n/world elements -> the exchange step is ONE kernel storing into the peers' buffers over
-    NVLink (twiddle + transpose fused in); otherwise twiddle kernel + NCCL all-to-all + transpose kernel."""
+    NVLink (twiddle + transpose fused in); otherwise twiddle kernel + NCCL all-to-all + transpose kernel.
+    fused (with peer): the exchange is the store phase of the first line pass itself -- one fused TMA kernel does lines,
+    twiddle and NVLink stores -- and the result comes back TRANSPOSED: this rank's [K][N2] block, out[k1 local][k2] =
+    X[k1 + N1 k2] (`gather_spectrum(..., fused=True)`)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n1, n2, k, w = split_1d(n, world)
     if slab.numel() != n1 * w:
         raise ValueError("slab has %d elements, expected %d" % (slab.numel(), n1 * w))
+    if peer is not None and fused:
+        out = work if work is not None else ops.empty(n1 * w)
+        peer.fence()                                      # every rank is done reading its receive buffer (previous call)
+        peer.lines_peer(slab, n1, w, _ilog2(n))           # lines over n1 + twiddle + NVLink stores: receive buffers [world][K][W]
+        peer.fence()                                      # every rank's stores have landed
+        peer.rows_seg(out, n2, k)                         # lines over n2 on segmented rows -> [K][N2]
+        return out
     if peer is not None:
         out = work if work is not None else ops.empty(n1 * w)
         peer.fence()                                      # every rank is done reading its receive buffer (previous call)
@@ -203,10 +226,13 @@ def scatter_signal(x, n, rank, world):
     return x.view(n1, n2)[:, rank * w:(rank + 1) * w].contiguous().view(-1)
 
 
-def gather_spectrum(slabs, n):
-    """Natural-order spectrum from the per-rank [N2][K] slabs (list in rank order)."""
+def gather_spectrum(slabs, n, fused=False):
+    """Natural-order spectrum from the per-rank [N2][K] slabs (list in rank order); fused: from the [K][N2] blocks of
+    fft_1d_sharded(fused=True)."""
     world = len(slabs)
     n1, n2, k, _ = split_1d(n, world)
+    if fused:
+        return torch.cat([s.view(k, n2) for s in slabs], dim=0).t().contiguous().view(-1)
     return torch.cat([s.view(n2, k) for s in slabs], dim=1).contiguous().view(-1)
 
 

@@ -102,3 +102,68 @@ def test_sharded_paths_two_ranks(log2n, rows, cols):
     if torch.cuda.device_count() < 2:
         pytest.skip("one GPU visible; the 2-rank NCCL run needs `gpurun --gpus 2`")
     _run(2, log2n, rows, cols)
+
+
+def _fused_worker(rank, world, port, log2n, path, out):
+    """fft_1d_sharded(fused=True): lines + twiddle + NVLink stores in one kernel, segmented rows; this rank's [K][N2] block against
+    the oracle spectrum (a .npy the parent wrote), twice (receive-buffer reuse), and against the unfused peer-memory formulation."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "go-dsp_b200"))
+    import torch
+    import torch.distributed as dist
+    from godsp import distributed as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ops = D.DeviceOps()
+    n = 1 << log2n
+    n1, n2, k, w = D.split_1d(n, world)
+    x = torch.from_numpy(oracle.splitmix_complex(n, 6))
+    slab = D.scatter_signal(x, n, rank, world).cuda()
+    keep = slab.clone()
+    px = D.PeerExchange(n // world, ops)
+    assert px.fused_supported(n1, n2)
+    got = D.fft_1d_sharded(slab, n, ops, peer=px, fused=True).clone()
+    got2 = D.fft_1d_sharded(slab, n, ops, peer=px, fused=True).clone()
+    plain = D.fft_1d_sharded(slab, n, ops, peer=px).clone()            # [N2][K]
+    torch.cuda.synchronize()
+    assert torch.equal(slab, keep), "the input slab was modified"
+    assert torch.equal(got, got2)
+    want = torch.from_numpy(np.load(path, mmap_mode="r").reshape(n2, n1)[:, rank * k:(rank + 1) * k].T.copy()).cuda()
+    err = float((got.view(k, n2) - want).norm() / want.norm())
+    err_plain = float((got.view(k, n2) - plain.view(n2, k).t()).norm() / want.norm())
+    px.close()
+    out[rank] = (err, err_plain)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_fused(world, log2n, tmp_path):
+    import torch.multiprocessing as mp
+    n = 1 << log2n
+    path = str(tmp_path / "want.npy")
+    np.save(path, oracle.fft(oracle.splitmix_complex(n, 6)))
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fused_worker, args=(world, _free_port(), log2n, path, out), nprocs=world, join=True)
+    for r in range(world):
+        assert out[r][0] <= TOL and out[r][1] <= 1e-13, (r, out[r])
+
+
+def test_sharded_fused_exchange_one_rank(tmp_path):       # 2^26 = 2^13 x 2^13: the smallest size both line passes are fused for
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: these tests must run on the GPU box (there is no CPU fallback)")
+    _run_fused(1, 26, tmp_path)
+
+
+@pytest.mark.parametrize("log2n", [26, 27])
+def test_sharded_fused_exchange_two_ranks(log2n, tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: these tests must run on the GPU box (there is no CPU fallback)")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible; the 2-rank run needs `gpurun --gpus 2`")
+    _run_fused(2, log2n, tmp_path)

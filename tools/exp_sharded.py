@@ -52,8 +52,14 @@ for combo in (sys.argv[1:] or [""]):
     tex = timeit(lambda: (px.fence(), px.exchange(work, n1, w, lg), px.fence()))
     tl2 = timeit(lambda: ops.fft_strided(px.recv, work, 1, n2, k, 1))
     t2 = timeit(lambda: D.fft2_sharded(m, R, Cc, ops, peers=peers, out=res), reps=5)
+    # the exchange fused into the first line pass (TMA stores into the peers' receive buffers), segmented rows
+    fused = {}
+    if px.fused_supported(n1, n2):
+        fused["fft1d_fused_ms"] = timeit(lambda: D.fft_1d_sharded(src, n, ops, work=work, peer=px, fused=True))
+        fused["lines_peer_alone_ms"] = timeit(lambda: (px.fence(), px.lines_peer(src, n1, w, lg), px.fence()))
+        fused["rows_seg_alone_ms"] = timeit(lambda: px.rows_seg(work, n2, k))
     if rank == 0:
         print(json.dumps({"opts": combo, "world": world, "fft1d_log2n": lg, "fft1d_ms": t1, "lines1_alone_ms": tl1, "exchange_alone_ms": tex,
-                          "lines2_alone_ms": tl2, "fft2_sharded_ms": t2}), flush=True)
+                          "lines2_alone_ms": tl2, "fft2_sharded_ms": t2, **fused}), flush=True)
 px.close(); peers[0].close(); peers[1].close()
 dist.destroy_process_group()
