@@ -641,7 +641,7 @@ def run_fft2(args, torch, dist, L, sp, world, rank, timed, hbm_peak):
             "clocks": clocks, "_launches": int(launches)}
 
 
-def sharded_1d_kat(torch, dist, D, ops, px, n, world, rank, src, work):
+def sharded_1d_kat(torch, dist, D, ops, px, n, world, rank, src, work, fused=False):
     """Known-answer test at the full size: x[n] = delta[n - p] + sum_t a exp(2 pi i f_t n / N) (integer bins f_t), so
     X[k] = exp(-2 pi i p k / N) + N a [k == f_t]. Built and checked on the device in exact integer phase arithmetic."""
     n1, n2, k, w = D.split_1d(n, world)
@@ -657,15 +657,19 @@ def sharded_1d_kat(torch, dist, D, ops, px, n, world, rank, src, work):
             ang = (2.0 * np.pi / n) * ((idx * f) & mask).double()
             acc += amp * torch.complex(torch.cos(ang), torch.sin(ang))
         s2[a:a + rows] = acc
-    D.fft_1d_sharded(src, n, ops, work=work, peer=px)
+    D.fft_1d_sharded(src, n, ops, work=work, peer=px, fused=fused)
     torch.cuda.synchronize()
-    o2 = work.view(n2, k)
+    o2 = work.view(k, n2) if fused else work.view(n2, k)       # fused: [k1 local][k2], else [k2][k1 local]
     num = torch.zeros((), dtype=torch.float64, device="cuda")
     den = torch.zeros((), dtype=torch.float64, device="cuda")
-    rows = max(1, (1 << 24) // k)
-    for a in range(0, n2, rows):
-        k2 = torch.arange(a, min(n2, a + rows), dtype=torch.int64, device="cuda")[:, None]
-        kk = (rank * k + torch.arange(k, dtype=torch.int64, device="cuda"))[None, :] + n1 * k2
+    rows = max(1, (1 << 24) // (n2 if fused else k))
+    for a in range(0, k if fused else n2, rows):
+        if fused:
+            k1 = (rank * k + torch.arange(a, min(k, a + rows), dtype=torch.int64, device="cuda"))[:, None]
+            kk = k1 + n1 * torch.arange(n2, dtype=torch.int64, device="cuda")[None, :]
+        else:
+            k2 = torch.arange(a, min(n2, a + rows), dtype=torch.int64, device="cuda")[:, None]
+            kk = (rank * k + torch.arange(k, dtype=torch.int64, device="cuda"))[None, :] + n1 * k2
         ang = (-2.0 * np.pi / n) * ((kk * p) & mask).double()
         want = torch.complex(torch.cos(ang), torch.sin(ang))
         for f in tones:
@@ -678,7 +682,7 @@ def sharded_1d_kat(torch, dist, D, ops, px, n, world, rank, src, work):
     return float(torch.sqrt(t[0] / t[1]).item())
 
 
-def sharded_1d_vs_oracle(torch, dist, D, ops, world, rank, lg=24):
+def sharded_1d_vs_oracle(torch, dist, D, ops, world, rank, lg=24, fused=False):
     """the same peer-memory code path at 2^lg points against oracle.fft (rank 0 compares the gathered spectrum)"""
     import oracle
     n = 1 << lg
@@ -686,13 +690,14 @@ def sharded_1d_vs_oracle(torch, dist, D, ops, world, rank, lg=24):
     x = oracle.splitmix_complex(n, 6)
     slab = D.scatter_signal(torch.from_numpy(x), n, rank, world).cuda()
     px = D.PeerExchange(n1 * w, ops)
-    out = D.fft_1d_sharded(slab, n, ops, peer=px)
+    fused = fused and px.fused_supported(n1, n2)
+    out = D.fft_1d_sharded(slab, n, ops, peer=px, fused=fused)
     torch.cuda.synchronize()
     slabs = [torch.empty_like(out) for _ in range(world)]
     dist.all_gather(slabs, out)
     err = 0.0
     if rank == 0:
-        err = rel_l2(D.gather_spectrum(slabs, n).cpu().numpy(), oracle.fft(x))
+        err = rel_l2(D.gather_spectrum(slabs, n, fused=fused).cpu().numpy(), oracle.fft(x))
     px.close()
     return allmax(torch, dist, world, err)
 
@@ -720,8 +725,16 @@ def run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed):
     ms_nccl, _, _ = timed(step_nccl, steps, warmup)
     px = D.PeerExchange(n1 * w, ops)
 
+    fused = px.fused_supported(n1, n2)
+
+    def step_separate():
+        D.fft_1d_sharded(src, n, ops, work=work, peer=px)       # the peer-memory paths leave their input untouched
+
     def step():
-        D.fft_1d_sharded(src, n, ops, work=work, peer=px)       # the peer-memory path leaves its input untouched
+        D.fft_1d_sharded(src, n, ops, work=work, peer=px, fused=fused)
+    ms_sep = None
+    if fused:
+        ms_sep, _, _ = timed(step_separate, steps, warmup)
     ms, launches, clocks = timed(step, steps, warmup)
     # per phase, outside the timed region (CUDA events on the ops stream, every phase between two rendezvous, max over ranks)
     def phase_ms(fn):
@@ -733,27 +746,38 @@ def run_fft1d_sharded(args, torch, dist, L, sp, world, rank, timed):
         e1.record()
         torch.cuda.synchronize()
         return allmax(torch, dist, world, e0.elapsed_time(e1))
-    phases = {"lines_n1_ms": phase_ms(lambda: ops.fft_strided(src, work, 1, n1, w, 1)),
-              "twiddle_transpose_nvlink_stores_ms": phase_ms(lambda: px.exchange(work, n1, w, lg)),
-              "lines_n2_ms": phase_ms(lambda: ops.fft_strided(px.recv, work, 1, n2, k, 1))}
+    if fused:
+        phases = {"lines_n1_twiddle_nvlink_stores_ms": phase_ms(lambda: px.lines_peer(src, n1, w, lg)),
+                  "lines_n2_segmented_rows_ms": phase_ms(lambda: px.rows_seg(work, n2, k))}
+        t_x, t_l = phases["lines_n1_twiddle_nvlink_stores_ms"], phases["lines_n2_segmented_rows_ms"]
+    else:
+        phases = {"lines_n1_ms": phase_ms(lambda: ops.fft_strided(src, work, 1, n1, w, 1)),
+                  "twiddle_transpose_nvlink_stores_ms": phase_ms(lambda: px.exchange(work, n1, w, lg)),
+                  "lines_n2_ms": phase_ms(lambda: ops.fft_strided(px.recv, work, 1, n2, k, 1))}
+        t_x, t_l = phases["twiddle_transpose_nvlink_stores_ms"], phases["lines_n1_ms"]
     nv_bytes = 16 * (n // world) * (world - 1) // world
-    phases["nvlink_out_gbs_per_gpu"] = nv_bytes / (phases["twiddle_transpose_nvlink_stores_ms"] * 1e-3) / 1e9 if world > 1 else 0.0
-    phases["lines_hbm_frac"] = 32.0 * (n // world) / (phases["lines_n1_ms"] * 1e-3) / 1e9 / peaks()[0]
+    phases["nvlink_out_gbs_per_gpu"] = nv_bytes / (t_x * 1e-3) / 1e9 if world > 1 else 0.0
+    phases["lines_hbm_frac"] = 32.0 * (n // world) / (t_l * 1e-3) / 1e9 / peaks()[0]
     step()                                                      # `work` holds the whole transform again
     torch.cuda.synchronize()
     # Parseval on the last step: sum |X|^2 = n * sum |x|^2 over all ranks
     e = torch.stack([(work.real ** 2 + work.imag ** 2).sum(), (src.real ** 2 + src.imag ** 2).sum()])
     dist.all_reduce(e)
     parseval = abs(float(e[0].item()) / (n * float(e[1].item())) - 1.0)
-    kat = sharded_1d_kat(torch, dist, D, ops, px, n, world, rank, src, work)
+    kat = sharded_1d_kat(torch, dist, D, ops, px, n, world, rank, src, work, fused=fused)
     small = sharded_1d_vs_oracle(torch, dist, D, ops, world, rank, 24)
-    par = {"max_rel_l2": max(kat, small), "kat_full_size_rel_l2": kat, "oracle_2p24_rel_l2": small, "parseval_rel_err": parseval,
-           "vs": "impulse + three integer-bin tones at the full 2^%d points (closed form, exact integer phases); the same "
-                 "peer-memory path at 2^24 points vs oracle.fft" % lg}
+    small_fused = sharded_1d_vs_oracle(torch, dist, D, ops, world, rank, 26, fused=True) if fused else 0.0
+    par = {"max_rel_l2": max(kat, small, small_fused), "kat_full_size_rel_l2": kat, "oracle_2p24_rel_l2": small,
+           "oracle_2p26_fused_rel_l2": small_fused, "parseval_rel_err": parseval,
+           "vs": "impulse + three integer-bin tones at the full 2^%d points through the timed path (closed form, exact integer phases); the "
+                 "separate-exchange path at 2^24 points and the fused path at 2^26 points vs oracle.fft" % lg}
     return {"_parity": par, "metric": "single 1-D FFT GS/s (complex128, 2^%d points over %d GPUs)" % (lg, world), "value": n / (ms * 1e-3) / 1e9,
             "unit": "GS/s", "ms_per_step": ms, "scaling": "weak", "log2n": lg,
-            "api": "godsp.distributed.fft_1d_sharded(peer=PeerExchange): strided lines, ONE kernel for twiddle + transpose + NVLink P2P stores into the peers' buffers (gd_fourstep_exchange_dev), strided lines",
-            "nccl_all_to_all_variant_ms": ms_nccl, "phases": phases,
+            "api": ("godsp.distributed.fft_1d_sharded(peer=PeerExchange, fused=True): ONE fused TMA kernel for the length-N1 lines, the outer twiddle and the exchange "
+                    "(its pass-2 stores go through one tensor map per rank into the ranks' receive buffers over NVLink; gd_fourstep_lines_peer_dev), then the "
+                    "length-N2 lines on segmented rows (gd_fourstep_rows_seg_dev); result layout [K][N2]") if fused else
+                   "godsp.distributed.fft_1d_sharded(peer=PeerExchange): strided lines, ONE kernel for twiddle + transpose + NVLink P2P stores into the peers' buffers (gd_fourstep_exchange_dev), strided lines",
+            "nccl_all_to_all_variant_ms": ms_nccl, "separate_exchange_kernel_variant_ms": ms_sep, "phases": phases,
             "all_to_all_bytes_per_gpu": nv_bytes,
             "parseval_rel_err": parseval,
             "clocks": clocks, "_launches": int(launches), "_peer": px}
