@@ -1017,17 +1017,18 @@ int gd_fourstep_fused_supported(int64_t n1, int64_t n2, int world) {
     GD_ENTER();
     return fourstep_fused_supported(d, n1, n2, world) ? 1 : 0;
 }
-int gd_fourstep_lines_peer_dev(const double* slab, void* const* peer_recv, int64_t n1, int64_t w, int rank, int world, int log2n, void* stream) {
-    if (!slab || !peer_recv) return (int)invalid_arg("fourstep_lines_peer_dev: null");
+int gd_fourstep_lines_peer_dev(const double* slab, void* const* peer_recv, int64_t n1, int64_t w, int rank, int world, int log2n, int dir,
+                               void* stream) {
+    if (!slab || !peer_recv || (dir != 1 && dir != -1)) return (int)invalid_arg("fourstep_lines_peer_dev: null");
     GD_ENTER();
     ScratchOrder order__(d, pick(d, stream));
-    return (int)fourstep_lines_peer(d, (const cpx*)slab, (cpx* const*)peer_recv, n1, w, rank, world, log2n, pick(d, stream));
+    return (int)fourstep_lines_peer(d, (const cpx*)slab, (cpx* const*)peer_recv, n1, w, rank, world, log2n, dir, pick(d, stream));
 }
-int gd_fourstep_rows_seg_dev(const double* recv, double* out, int64_t n2, int64_t k, int world, void* stream) {
-    if (!recv || !out) return (int)invalid_arg("fourstep_rows_seg_dev: null");
+int gd_fourstep_rows_seg_dev(const double* recv, double* out, int64_t n2, int64_t k, int world, int dir, void* stream) {
+    if (!recv || !out || (dir != 1 && dir != -1)) return (int)invalid_arg("fourstep_rows_seg_dev: null");
     GD_ENTER();
     ScratchOrder order__(d, pick(d, stream));
-    return (int)fourstep_rows_seg(d, (const cpx*)recv, (cpx*)out, n2, k, world, pick(d, stream));
+    return (int)fourstep_rows_seg(d, (const cpx*)recv, (cpx*)out, n2, k, world, dir, pick(d, stream));
 }
 int gd_peer_block_copy_dev(const double* src, void* const* peers, int world, int rank, int64_t rows, int64_t cols, int64_t src_step,
                            int64_t src_pitch, int64_t dst_off, int64_t dst_pitch, void* stream) {

@@ -831,27 +831,29 @@ bool fourstep_fused_supported(Device& d, long long n1, long long n2, int world) 
            (world == 1 || (la2 % world == 0 && world % 2 == 0)) && w < (1LL << 30);
 }
 Status fourstep_lines_peer(Device& d, const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,
-                           cudaStream_t st) {
-    if (!slab || !peer_recv || rank < 0 || rank >= world || !fourstep_fused_supported(d, n1, (1LL << log2n) / n1, world) || w * world * n1 != (1LL << log2n))
+                           int dir, cudaStream_t st) {
+    // log2n = 0: no twiddle (the column pass of FFT2 on row blocks: rows [h*K, (h+1)*K) of the transformed slab go to rank h)
+    const long long n2 = log2n ? (1LL << log2n) / n1 : w * world;
+    if (!slab || !peer_recv || rank < 0 || rank >= world || !fourstep_fused_supported(d, n1, n2, world) || (log2n && w * world * n1 != (1LL << log2n)))
         return invalid("fourstep_lines_peer: unsupported shape (see gd_fourstep_fused_supported)");
     const Tma2dEntry* te = tma2d_entry(d, ilog2ll(n1));
     if (!te->cols_ok(slab, slab, n1, w, w)) return invalid("fourstep_lines_peer: slab alignment");
     Tma2dExtra ex;
     ex.tw2_log2m = log2n; ex.tw2_col0 = (long long)rank * w;
     ex.npeer = world; ex.peer = peer_recv; ex.peer_off = (long long)rank * (n1 / world) * w;
-    return te->run(d, 1, slab, w, const_cast<cpx*>(slab), w, w, false, 1.0, st, ex);
+    return te->run(d, 1, slab, w, const_cast<cpx*>(slab), w, w, dir < 0, dir < 0 ? 1.0 / (double)n1 : 1.0, st, ex);
 }
 // Second half: this rank's receive buffer [world][K][w] -- row k1 of the spectrum's [n1][n2] view in `world` segments of w = n2 / world
 // points -- through the fused family in row mode on segmented lines: out[k1 local][k2] = X[k1 + n1 k2], K transforms of n2 points.
-Status fourstep_rows_seg(Device& d, const cpx* recv, cpx* out, long long n2, long long k, int world, cudaStream_t st) {
+Status fourstep_rows_seg(Device& d, const cpx* recv, cpx* out, long long n2, long long k, int world, int dir, cudaStream_t st) {
     if (!recv || !out || recv == out || world < 1 || n2 % world) return invalid("fourstep_rows_seg: bad arguments");
     const long long w = n2 / world;
-    if (world == 1) { FusedOps none; return fft_pow2(d, recv, n2, out, n2, ilog2ll(n2), k, none, st); }
+    if (world == 1) return fft1d(d, recv, n2, out, n2, n2, k, false, dir, st);
     const Tma2dEntry* te = is_pow2(n2) ? tma2d_entry(d, ilog2ll(n2)) : nullptr;
     if (!te || k % te->unit || ((uintptr_t)recv % 16) || ((uintptr_t)out % 16)) return invalid("fourstep_rows_seg: unsupported shape (see gd_fourstep_fused_supported)");
     Tma2dExtra ex;
     ex.seg = world; ex.seg_dist = k * w;
-    return te->run(d, 0, recv, w, out, n2, k, false, 1.0, st, ex);
+    return te->run(d, 0, recv, w, out, n2, k, dir < 0, dir < 0 ? 1.0 / (double)n2 : 1.0, st, ex);
 }
 
 // FFT2 on row blocks: both exchanges are strided block copies into peer memory (no repack kernels, no NCCL data

@@ -191,8 +191,8 @@ struct Tma2dExtra {
     long long seg_dist = 0;
 };
 bool fourstep_fused_supported(Device& d, long long n1, long long n2, int world);
-Status fourstep_lines_peer(Device& d, const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n, cudaStream_t st);
-Status fourstep_rows_seg(Device& d, const cpx* recv, cpx* out, long long n2, long long k, int world, cudaStream_t st);
+Status fourstep_lines_peer(Device& d, const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n, int dir, cudaStream_t st);
+Status fourstep_rows_seg(Device& d, const cpx* recv, cpx* out, long long n2, long long k, int world, int dir, cudaStream_t st);
 Status fourstep_twiddle(cpx* blk, long long rows, long long cols, long long row0, long long col0, int log2n, cudaStream_t st, int dir = 1);
 Status repack_gkw(const cpx* in, cpx* out, long long G, long long K, long long W, cudaStream_t st);
 Status fourstep_exchange(const cpx* slab, cpx* const* peer_recv, long long n1, long long w, int rank, int world, int log2n,

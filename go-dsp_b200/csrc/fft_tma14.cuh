@@ -362,7 +362,7 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             if (INV) tb0 = make_double2(tb0.x * a.scale, tb0.y * a.scale);
         }
         if constexpr (TW2 != 0 && MODE == T14_COLS) {
-            if (wi.type == 1) {
+            if (wi.type == 1 && a.tw2_log2m > 0) {
                 // outer twiddle of this line's outputs k = k1 + LA k2, k2 = KB j' + k_lo + 32 m: w^(col (k1 + LA KB j')), w^(col LA), w^(32 col LA)
                 const unsigned long long mask = (1ULL << a.tw2_log2m) - 1ULL;
                 const unsigned long long col = (unsigned long long)a.tw2_col0 +
@@ -427,7 +427,7 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     for (int m = 0; m < NJ; m++) s[(kl + 32 * m) * LINES] = x[NJ * kl + m];
             }
         } else {
-            if constexpr (TW2 != 0 && MODE == T14_COLS) {
+            if (TW2 != 0 && MODE == T14_COLS && a.tw2_log2m > 0) {       // tw2_log2m = 0 with TW2 = 2: peer stores without a twiddle (FFT2)
                 cpx c[KB];
                 c[0] = tb0;
 #pragma unroll

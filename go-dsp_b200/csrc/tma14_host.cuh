@@ -82,7 +82,7 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
     const int tw2_log2m = ex.tw2_log2m;
     const long long tw2_col0 = ex.tw2_col0, in_mdist = ex.in_mdist, out_mdist = ex.out_mdist;
     long long nmat = ex.nmat;
-    if (ex.npeer && (mode != T14_COLS || !tw2_log2m || ex.npeer > 8 || (int)LB % ex.npeer || !ex.peer || nmat > 1)) return invalid14("fused kernel: bad peer-store launch");
+    if (ex.npeer && (mode != T14_COLS || ex.npeer > 8 || (int)LB % ex.npeer || !ex.peer || nmat > 1)) return invalid14("fused kernel: bad peer-store launch");
     if (ex.seg > 1 && (mode != T14_ROWS || LA > 512 || (int)LA % ex.seg || (ex.seg & 1))) return invalid14("fused kernel: bad segmented-row launch");
     using SH = T14Shape<LA, LB>;
     constexpr cuuint64_t A = LA, Bq = LB, N = SH::N, LNA = SH::LINES_A, LNB = SH::LINES_B, UNIT = SH::UNIT;
@@ -212,7 +212,7 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         const int sms = d.tma_grid_cap > 0 && d.tma_grid_cap < d.num_sms ? d.tma_grid_cap : d.num_sms;
         const int grid = (int)(nitems < sms ? nitems : sms);
         if constexpr (LB <= 256) {
-            if (tw2_log2m && ex.npeer) e = inv ? launch14<LA, LB, T14_COLS, true, false, 2>(grid, m_x, m_int, m_out, f, st, &peer_maps) : launch14<LA, LB, T14_COLS, false, false, 2>(grid, m_x, m_int, m_out, f, st, &peer_maps);
+            if (ex.npeer) e = inv ? launch14<LA, LB, T14_COLS, true, false, 2>(grid, m_x, m_int, m_out, f, st, &peer_maps) : launch14<LA, LB, T14_COLS, false, false, 2>(grid, m_x, m_int, m_out, f, st, &peer_maps);
             else if (tw2_log2m) e = inv ? launch14<LA, LB, T14_COLS, true, false, 1>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, false, 1>(grid, m_x, m_int, m_out, f, st);
             else if (f.prof && !inv && LA == LB) e = mode == T14_ROWS ? launch14<LA, LB, T14_ROWS, false, LA == LB>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, LA == LB>(grid, m_x, m_int, m_out, f, st);
             else if (mode == T14_ROWS) e = inv ? launch14<LA, LB, T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);

@@ -49,8 +49,8 @@ SIGNATURES = {
     "gd_fourstep_exchange_dev": (_int, [_vp, C.POINTER(_vp), _i64, _i64, _int, _int, _int, _vp]),
     "gd_fourstep_lines_exchange_dev": (_int, [_vp, _vp, C.POINTER(_vp), _i64, _i64, _int, _int, _int, _vp]),
     "gd_fourstep_fused_supported": (_int, [_i64, _i64, _int]),
-    "gd_fourstep_lines_peer_dev": (_int, [_vp, C.POINTER(_vp), _i64, _i64, _int, _int, _int, _vp]),
-    "gd_fourstep_rows_seg_dev": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
+    "gd_fourstep_lines_peer_dev": (_int, [_vp, C.POINTER(_vp), _i64, _i64, _int, _int, _int, _int, _vp]),
+    "gd_fourstep_rows_seg_dev": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp]),
     "gd_peer_block_copy_dev": (_int, [_vp, C.POINTER(_vp), _int, _int, _i64, _i64, _i64, _i64, _i64, _i64, _vp]),
     "gd_ipc_alloc": (_int, [C.POINTER(_vp), _sz, C.c_char_p]), "gd_ipc_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
     "gd_ipc_close": (_int, [_vp]),

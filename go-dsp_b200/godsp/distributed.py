@@ -134,14 +134,14 @@ class PeerExchange:
         """both line lengths are in the range of the fused TMA kernel for this world size (gd_fourstep_fused_supported)"""
         return self.L.gd_fourstep_fused_supported(n1, n2, self.world) == 1
 
-    def lines_peer(self, slab, n1, w, log2n):
-        """length-n1 lines of the slab, outer twiddle, and the exchange as the kernel's own TMA stores into every rank's
-        receive buffer over NVLink: receive buffers become [world][K][w] (gd_fourstep_lines_peer_dev)"""
-        _capi.check(self.L.gd_fourstep_lines_peer_dev(slab.data_ptr(), self.ptr_array, n1, w, self.rank, self.world, log2n, self.ops._sp()))
+    def lines_peer(self, slab, n1, w, log2n, direction=1):
+        """length-n1 lines of the slab, outer twiddle (log2n = 0: none), and the exchange as the kernel's own TMA stores into
+        every rank's receive buffer over NVLink: receive buffers become [world][K][w] (gd_fourstep_lines_peer_dev)"""
+        _capi.check(self.L.gd_fourstep_lines_peer_dev(slab.data_ptr(), self.ptr_array, n1, w, self.rank, self.world, log2n, direction, self.ops._sp()))
 
-    def rows_seg(self, out, n2, k):
+    def rows_seg(self, out, n2, k, direction=1):
         """the K rows of the receive buffer (n2 points each, in `world` segments) -> out[K][n2] (gd_fourstep_rows_seg_dev)"""
-        _capi.check(self.L.gd_fourstep_rows_seg_dev(self.recv.data_ptr(), out.data_ptr(), n2, k, self.world, self.ops._sp()))
+        _capi.check(self.L.gd_fourstep_rows_seg_dev(self.recv.data_ptr(), out.data_ptr(), n2, k, self.world, direction, self.ops._sp()))
 
     def block_copy(self, src, rows, cols, src_step, src_pitch, dst_off, dst_pitch):
         """every peer h: peer_buffer[h][dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c]"""
@@ -236,11 +236,12 @@ def gather_spectrum(slabs, n, fused=False):
     return torch.cat([s.view(n2, k) for s in slabs], dim=1).contiguous().view(-1)
 
 
-def fft2_sharded(block, rows, cols, ops, group=None, direction=1, peers=None, out=None):
+def fft2_sharded(block, rows, cols, ops, group=None, direction=1, peers=None, out=None, fused=True):
     """fft.FFT2 / IFFT2 of a rows x cols matrix; `block` is this rank's [rows/world][cols] row block
     (flattened complex128, overwritten).  Returns the rank's row block of the result.
     peers: (PeerExchange, PeerExchange) of rows*cols/world elements each -> both exchanges are block copies into the
-    peers' buffers over NVLink (gd_peer_block_copy_dev), no repack kernels and no NCCL data movement."""
+    peers' buffers over NVLink (gd_peer_block_copy_dev), no repack kernels and no NCCL data movement; with `fused` (and
+    shapes in the fused kernel's range) the second exchange disappears into the store phase of the column pass."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if rows % world or cols % world:
         raise ValueError("world size %d must divide %d x %d" % (world, rows, cols))
@@ -253,6 +254,14 @@ def fft2_sharded(block, rows, cols, ops, group=None, direction=1, peers=None, ou
         # my columns [h*wc, (h+1)*wc) of my rows -> rank h's column slab [rows][wc], rows [rank*rg, (rank+1)*rg)
         colp.block_copy(block, rg, wc, wc, cols, rank * rg * wc, wc)
         colp.fence()
+        if fused and rowp.fused_supported(rows, cols):
+            # every column (fft/fft.go:138-144) through the fused TMA kernel whose stores ARE the second exchange: rows
+            # [h*rg, (h+1)*rg) of my column slab land in rank h's buffer as block `rank` of [world][rg][wc]; then every row
+            # (fft.go:146-151) on segmented rows -> this rank's [rg][cols] row block
+            rowp.lines_peer(colp.recv, rows, wc, 0, direction)
+            rowp.fence()
+            rowp.rows_seg(res, cols, rg, direction)
+            return res
         ops.fft_strided(colp.recv, colp.recv, 1, rows, wc, direction)    # every column (fft/fft.go:138-144)
         # rows [h*rg, (h+1)*rg) of my column slab -> rank h's row block [rg][cols], columns [rank*wc, (rank+1)*wc)
         rowp.block_copy(colp.recv, rg, wc, rg * wc, wc, rank * wc, cols)

@@ -165,11 +165,13 @@ GD_API int gd_fourstep_lines_exchange_dev(const double* slab_dev, double* tmp_de
  * transforms the K rows of a receive buffer -- each n2 = world*w points in `world` segments -- into out[k1 local][k2] =
  * X[k1 + n1*k2] ([K][n2]). gd_fourstep_fused_supported: 1 when both line lengths are in the fused kernel's range for this
  * world size (n1 = 2^13..2^17, n2 = 2^13..2^18, world 1, 2, 4 or 8). Same rendezvous rules as gd_fourstep_exchange_dev.
- * Replaces the log2(N) sweeps of fft/radix2.go:131-151 for one transform spread over the GPUs of a node. */
+ * dir = -1: inverse lines (1/length each) and the conjugate twiddle. log2n = 0: no twiddle -- the column pass of fft.FFT2 on row
+ * blocks (fft/fft.go:138-144) whose stores land in the ranks' row blocks, followed by the row pass (fft.go:146-151) on segmented
+ * rows. Replaces the log2(N) sweeps of fft/radix2.go:131-151 for one transform spread over the GPUs of a node. */
 GD_API int gd_fourstep_fused_supported(int64_t n1, int64_t n2, int world);
 GD_API int gd_fourstep_lines_peer_dev(const double* slab_dev, void* const* peer_recv, int64_t n1, int64_t w, int rank, int world, int log2n,
-                                      void* stream);
-GD_API int gd_fourstep_rows_seg_dev(const double* recv_dev, double* out_dev, int64_t n2, int64_t k, int world, void* stream);
+                                      int dir, void* stream);
+GD_API int gd_fourstep_rows_seg_dev(const double* recv_dev, double* out_dev, int64_t n2, int64_t k, int world, int dir, void* stream);
 /* FFT2 on row blocks: an exchange as strided block copies into peer memory; for every peer h (complex128 elements):
  * peers[h][dst_off + r*dst_pitch + c] = src[h*src_step + r*src_pitch + c], r < rows, c < cols */
 GD_API int gd_peer_block_copy_dev(const double* src_dev, void* const* peers, int world, int rank, int64_t rows, int64_t cols, int64_t src_step,

@@ -135,7 +135,25 @@ def _fused_worker(rank, world, port, log2n, path, out):
     err = float((got.view(k, n2) - want).norm() / want.norm())
     err_plain = float((got.view(k, n2) - plain.view(n2, k).t()).norm() / want.norm())
     px.close()
-    out[rank] = (err, err_plain)
+    # fft.FFT2 on row blocks, 8192 x 8192: the column pass whose stores are the second exchange + segmented rows give the bits of
+    # the block-copy formulation (same kernels, same arithmetic), forward and inverse
+    rows = cols = 8192
+    rg = rows // world
+    blk = torch.empty(rg * cols, dtype=torch.complex128, device="cuda")
+    from godsp import _capi as capi
+    capi.check(ops.L.gd_fill_splitmix_dev(blk.data_ptr(), 2 * rg * cols, 4, 2 * rank * rg * cols, ops._sp()))
+    pp = (D.PeerExchange(rg * cols, ops), D.PeerExchange(rg * cols, ops))
+    assert pp[1].fused_supported(rows, cols) or world == 1
+    keep2 = blk.clone()
+    res_f = D.fft2_sharded(blk.clone(), rows, cols, ops, peers=pp, fused=True).clone()
+    res_u = D.fft2_sharded(blk.clone(), rows, cols, ops, peers=pp, fused=False).clone()
+    back_f = D.fft2_sharded(res_f.clone(), rows, cols, ops, direction=-1, peers=pp, fused=True).clone()
+    torch.cuda.synchronize()
+    same = bool(torch.equal(res_f, res_u))
+    rt = float((back_f - keep2).norm() / keep2.norm())
+    pp[0].close()
+    pp[1].close()
+    out[rank] = (err, err_plain, same, rt)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -149,7 +167,7 @@ def _run_fused(world, log2n, tmp_path):
     out = mgr.dict()
     mp.spawn(_fused_worker, args=(world, _free_port(), log2n, path, out), nprocs=world, join=True)
     for r in range(world):
-        assert out[r][0] <= TOL and out[r][1] <= 1e-13, (r, out[r])
+        assert out[r][0] <= TOL and out[r][1] <= 1e-13 and out[r][2] and out[r][3] <= TOL, (r, out[r])
 
 
 def test_sharded_fused_exchange_one_rank(tmp_path):       # 2^26 = 2^13 x 2^13: the smallest size both line passes are fused for

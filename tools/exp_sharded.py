@@ -51,7 +51,8 @@ for combo in (sys.argv[1:] or [""]):
     tl1 = timeit(lambda: ops.fft_strided(src, work, 1, n1, w, 1))
     tex = timeit(lambda: (px.fence(), px.exchange(work, n1, w, lg), px.fence()))
     tl2 = timeit(lambda: ops.fft_strided(px.recv, work, 1, n2, k, 1))
-    t2 = timeit(lambda: D.fft2_sharded(m, R, Cc, ops, peers=peers, out=res), reps=5)
+    t2 = timeit(lambda: D.fft2_sharded(m, R, Cc, ops, peers=peers, out=res, fused=False), reps=5)
+    t2f = timeit(lambda: D.fft2_sharded(m, R, Cc, ops, peers=peers, out=res, fused=True), reps=5)
     # the exchange fused into the first line pass (TMA stores into the peers' receive buffers), segmented rows
     fused = {}
     if px.fused_supported(n1, n2):
@@ -60,6 +61,6 @@ for combo in (sys.argv[1:] or [""]):
         fused["rows_seg_alone_ms"] = timeit(lambda: px.rows_seg(work, n2, k))
     if rank == 0:
         print(json.dumps({"opts": combo, "world": world, "fft1d_log2n": lg, "fft1d_ms": t1, "lines1_alone_ms": tl1, "exchange_alone_ms": tex,
-                          "lines2_alone_ms": tl2, "fft2_sharded_ms": t2, **fused}), flush=True)
+                          "lines2_alone_ms": tl2, "fft2_sharded_ms": t2, "fft2_sharded_fused_ms": t2f, **fused}), flush=True)
 px.close(); peers[0].close(); peers[1].close()
 dist.destroy_process_group()
