@@ -840,7 +840,7 @@ Status fourstep_lines_peer(Device& d, const cpx* slab, cpx* const* peer_recv, lo
     if (!te->cols_ok(slab, slab, n1, w, w)) return invalid("fourstep_lines_peer: slab alignment");
     Tma2dExtra ex;
     ex.tw2_log2m = log2n; ex.tw2_col0 = (long long)rank * w;
-    ex.npeer = world; ex.peer = peer_recv; ex.peer_off = (long long)rank * (n1 / world) * w;
+    ex.npeer = world; ex.peer = peer_recv; ex.peer_off = (long long)rank * (n1 / world) * w; ex.rank = rank;
     return te->run(d, 1, slab, w, const_cast<cpx*>(slab), w, w, dir < 0, dir < 0 ? 1.0 / (double)n1 : 1.0, st, ex);
 }
 // Second half: this rank's receive buffer [world][K][w] -- row k1 of the spectrum's [n1][n2] view in `world` segments of w = n2 / world

@@ -187,6 +187,7 @@ struct Tma2dExtra {
     int npeer = 0;                   // COLS + tw2: rows of the output spread over npeer ranks' buffers (peer[h] + peer_off, row pitch out_dist)
     cpx* const* peer = nullptr;
     long long peer_off = 0;
+    int rank = 0;
     int seg = 0;                     // ROWS: a transform is seg segments, seg_dist elements apart
     long long seg_dist = 0;
 };

@@ -75,6 +75,7 @@ struct Tma14Params {
     long long tw2_col0;          //   column = tw2_col0 + the column's index in this launch, k = the output index in the line
     int bshift;                  // COLS: a launch over several matrices (dimension 3 of the maps) has 2^bshift phases per matrix; 31 = one matrix
     int npeer;                   // TW2 == 2: number of ranks G the rows of the output are spread over (T14Peers)
+    int prot;                    //   this rank: the boxes of a half tile go out in rotated order, so the ranks do not all store to the same peer at once
     int seg;                     // ROWS, > 0: a transform's LA rows of LB points are `seg` segments of LA / seg rows (dimension 2 of the input map)
 };
 // TW2 == 2 (COLS): the output rows k = k1 + LA k2 of the slab belong to rank k / (N / G): instead of one local output map the stores of
@@ -230,7 +231,8 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                         for (int hf = 0; hf < 2; hf++) {
                             t14_coords<LA, LB, MODE>(1, pi.tf, pi.c, hf, S, a.bshift, c0, c1, c2, c3, false);
 #pragma unroll 1
-                            for (int jb = 0; jb < nbox; jb++) {
+                            for (int jq = 0; jq < nbox; jq++) {
+                                const int jb = (jq + a.prot) % nbox;
                                 const int k2 = c2 + jb * rows;
                                 tma_store_4d(&peers.m[k2 / per], c0, c1, k2 % per, c3, srcb + (size_t)hf * HALF_ELEMS + (size_t)jb * rows * (4096 / LB));
                             }

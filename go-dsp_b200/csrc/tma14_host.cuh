@@ -198,7 +198,7 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.scale = scale;
         f.tw2_log2m = tw2_log2m; f.tw2_col0 = multi ? tw2_col0 : tw2_col0 + g0 * (long long)UNIT;
-        f.bshift = bshift; f.npeer = ex.npeer; f.seg = ex.seg > 1 ? ex.seg : 0;
+        f.bshift = bshift; f.npeer = ex.npeer; f.prot = ex.rank; f.seg = ex.seg > 1 ? ex.seg : 0;
         f.prof = nullptr;
         if (d.tma_prof) {
             long long* pr;
