@@ -342,6 +342,7 @@ static int set_option_one(Device& d, const char* key, int64_t value) {
     else if (!strcmp(key, "tma19")) d.use_tma19 = value != 0;
     else if (!strcmp(key, "huge_min_log2n")) { if (value < 19 || value > 25) return (int)invalid_arg("huge_min_log2n out of range"); d.huge_min_log2n = (int)value; }
     else if (!strcmp(key, "bluestein_stream")) d.bluestein_stream = value != 0;
+    else if (!strcmp(key, "bluestein_fuse_mul")) d.bluestein_fuse_mul = value != 0;
     else if (!strcmp(key, "bluestein_chunk_mb")) { if (value < 1 || value > 16384) return (int)invalid_arg("bluestein_chunk_mb out of range"); d.bluestein_chunk_bytes = (size_t)value << 20; }
     else if (!strcmp(key, "axis_single_max_log2")) { if (value < 4 || value > 12) return (int)invalid_arg("axis_single_max_log2 out of range"); d.axis_single_max_log2 = (int)value; }
     else if (!strcmp(key, "huge_l1")) { if (value != 0 && (value < 13 || value > 17)) return (int)invalid_arg("huge_l1 out of range"); d.huge_l1 = (int)value; }

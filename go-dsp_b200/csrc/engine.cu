@@ -982,13 +982,23 @@ static Status bluestein_fft(Device& d, const void* in, long long in_dist, cpx* o
             const void* src = real_in ? (const void*)((const double*)in + b0 * in_dist) : (const void*)((const cpx*)in + b0 * in_dist);
             bluestein_prep_kernel<<<g, 256, 0, st>>>(src, in_dist, real_in ? 1 : 0, dir < 0 ? 1 : 0, n, la, pl->chirp_inv, A);
             GD_CUDA(cudaGetLastError());
-            GD_TRY(fft_pow2(d, A, la, A, la, pl->log2la, nb, fwd, st));
-            bluestein_mul_kernel<<<g, 256, 0, st>>>(A, pl->bhat, la);
-            GD_CUDA(cudaGetLastError());
+            // forward transform with the product with FFT(b) on its stores where the fused family takes the whole chunk (padded length
+            // 2^14 .. 2^19, whole phases), else the transform and a product sweep
+            const Tma2dEntry* te = d.bluestein_fuse_mul ? tma2d_entry(d, pl->log2la) : nullptr;
+            if (te && nb % te->unit == 0 && te->rows_ok(A, la, A, la, nb, 0, 0, 1.0)) {
+                Tma2dExtra ex;
+                ex.aux = pl->bhat;
+                GD_TRY(te->run(d, 0, A, la, A, la, nb, false, 1.0, st, ex));
+            } else {
+                GD_TRY(fft_pow2(d, A, la, A, la, pl->log2la, nb, fwd, st));
+                bluestein_mul_kernel<<<g, 256, 0, st>>>(A, pl->bhat, la);
+                GD_CUDA(cudaGetLastError());
+                g_launches++;
+            }
             GD_TRY(fft_pow2(d, A, la, A, la, pl->log2la, nb, inv, st));
             bluestein_post_kernel<<<g, 256, 0, st>>>(A, la, pl->chirp_inv, n, dir < 0 ? 1 : 0, (double)n, out + b0 * out_dist, out_dist);
             GD_CUDA(cudaGetLastError());
-            g_launches += 3;
+            g_launches += 2;
         }
         return GD_OK;
     }

@@ -82,6 +82,7 @@ struct Device {
     void* scratch[SCR_NSLOTS] = {nullptr};
     size_t scratch_bytes[SCR_NSLOTS] = {0};
     size_t pass_scratch_budget = 1ull << 30;    // upper bound of the inter-pass scratch of the two-launch four-step path
+    bool bluestein_fuse_mul = true;             // ... with the product with FFT(b) on the stores of the forward transform (fused family sizes)
     bool bluestein_stream = true;               // padded length >= 2^14, at least 2^21 padded points per call: plain transforms + streaming kernels
     size_t bluestein_chunk_bytes = 1ull << 30;  // padded sequences of one Bluestein chunk (between its two transforms)
     size_t l2_block_budget = 24ull << 20;       // inter-pass block of one chunk: small enough to stay in L2 between the passes
@@ -188,6 +189,7 @@ struct Tma2dExtra {
     cpx* const* peer = nullptr;
     long long peer_off = 0;
     int rank = 0;
+    const cpx* aux = nullptr;        // ROWS, forward: output k of every transform leaves multiplied by aux[k]
     int seg = 0;                     // ROWS: a transform is seg segments, seg_dist elements apart
     long long seg_dist = 0;
 };

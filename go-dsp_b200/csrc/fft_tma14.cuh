@@ -25,6 +25,8 @@
 // column n2 leaves multiplied by w_M^(n2 k1), so the outer four-step's twiddle sweep disappears (fft_pow2_huge in engine.cu).
 // The three bases per thread and tile come from sincospi of exactly reduced exponents (no table above 2^24 entries).
 // TW2 = 2: the same, and the stores go to the ranks of a sharded transform (T14Peers below).
+// TW2 = 3 (ROWS): output k of every transform leaves multiplied by aux[k] (Bluestein's product with the cached FFT(b),
+// fft/fft.go:63-66: one sweep less than a separate product kernel; aux is L2 resident).
 #pragma once
 #include <type_traits>
 #include "fft_tma.cuh"
@@ -76,6 +78,7 @@ struct Tma14Params {
     int bshift;                  // COLS: a launch over several matrices (dimension 3 of the maps) has 2^bshift phases per matrix; 31 = one matrix
     int npeer;                   // TW2 == 2: number of ranks G the rows of the output are spread over (T14Peers)
     int prot;                    //   this rank: the boxes of a half tile go out in rotated order, so the ranks do not all store to the same peer at once
+    const cpx* aux;              // TW2 == 3 (ROWS): N factors, output k of every transform is multiplied by aux[k]
     int seg;                     // ROWS, > 0: a transform's LA rows of LB points are `seg` segments of LA / seg rows (dimension 2 of the input map)
 };
 // TW2 == 2 (COLS): the output rows k = k1 + LA k2 of the slab belong to rank k / (N / G): instead of one local output map the stores of
@@ -442,6 +445,14 @@ fft_tma14_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                         if (m < NJ - 1) c[kl] = cmul(c[kl], tb32);
                     }
                 }
+            }
+            if constexpr (TW2 == 3 && MODE == T14_ROWS) {
+                // k = k1 + LA k2, k1 = LINES (tile of the transform) + line, k2 = KB j' + k_lo + 32 m
+                const cpx* ap = a.aux + (size_t)((wi.c % SH::TPT) * LINES + ell) + (size_t)LA * (KB * j);
+#pragma unroll
+                for (int kl = 0; kl < KB; kl++)
+#pragma unroll
+                    for (int m = 0; m < NJ; m++) x[NJ * kl + m] = cmul(x[NJ * kl + m], __ldg(ap + (size_t)LA * (kl + 32 * m)));
             }
             cpx* s = wbuf + (KB * j) * LINES + ell;          // X[k2 = KB j + k_lo + 32 m]: row k2 of the tile, column = line
 #pragma unroll

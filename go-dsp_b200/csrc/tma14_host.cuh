@@ -83,6 +83,7 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
     const long long tw2_col0 = ex.tw2_col0, in_mdist = ex.in_mdist, out_mdist = ex.out_mdist;
     long long nmat = ex.nmat;
     if (ex.npeer && (mode != T14_COLS || ex.npeer > 8 || (int)LB % ex.npeer || !ex.peer || nmat > 1)) return invalid14("fused kernel: bad peer-store launch");
+    if (ex.aux && (mode != T14_ROWS || inv || tw2_log2m || ex.npeer)) return invalid14("fused kernel: the aux product needs forward row mode");
     if (ex.seg > 1 && (mode != T14_ROWS || LA > 512 || (int)LA % ex.seg || (ex.seg & 1))) return invalid14("fused kernel: bad segmented-row launch");
     using SH = T14Shape<LA, LB>;
     constexpr cuuint64_t A = LA, Bq = LB, N = SH::N, LNA = SH::LINES_A, LNB = SH::LINES_B, UNIT = SH::UNIT;
@@ -198,7 +199,7 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
         f.done1 = cnt; f.done2 = cnt + CH; f.queue = cnt + 2 * CH;
         f.tw_lo = tw.lo; f.tw_hi = tw.hi; f.scale = scale;
         f.tw2_log2m = tw2_log2m; f.tw2_col0 = multi ? tw2_col0 : tw2_col0 + g0 * (long long)UNIT;
-        f.bshift = bshift; f.npeer = ex.npeer; f.prot = ex.rank; f.seg = ex.seg > 1 ? ex.seg : 0;
+        f.bshift = bshift; f.npeer = ex.npeer; f.prot = ex.rank; f.aux = ex.aux; f.seg = ex.seg > 1 ? ex.seg : 0;
         f.prof = nullptr;
         if (d.tma_prof) {
             long long* pr;
@@ -215,11 +216,13 @@ static Status fft_tma_2d(Device& d, int mode, const cpx* in, long long in_dist, 
             if (ex.npeer) e = inv ? launch14<LA, LB, T14_COLS, true, false, 2>(grid, m_x, m_int, m_out, f, st, &peer_maps) : launch14<LA, LB, T14_COLS, false, false, 2>(grid, m_x, m_int, m_out, f, st, &peer_maps);
             else if (tw2_log2m) e = inv ? launch14<LA, LB, T14_COLS, true, false, 1>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, false, 1>(grid, m_x, m_int, m_out, f, st);
             else if (f.prof && !inv && LA == LB) e = mode == T14_ROWS ? launch14<LA, LB, T14_ROWS, false, LA == LB>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false, LA == LB>(grid, m_x, m_int, m_out, f, st);
+            else if (mode == T14_ROWS && ex.aux) e = launch14<LA, LB, T14_ROWS, false, false, 3>(grid, m_x, m_int, m_out, f, st);
             else if (mode == T14_ROWS) e = inv ? launch14<LA, LB, T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
             else e = inv ? launch14<LA, LB, T14_COLS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_COLS, false>(grid, m_x, m_int, m_out, f, st);
         } else {
             if (mode != T14_ROWS) { rc = invalid14("fused kernel: columns need LB <= 256"); break; }
-            e = inv ? launch14<LA, LB, T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
+            if (ex.aux) e = launch14<LA, LB, T14_ROWS, false, false, 3>(grid, m_x, m_int, m_out, f, st);
+            else e = inv ? launch14<LA, LB, T14_ROWS, true>(grid, m_x, m_int, m_out, f, st) : launch14<LA, LB, T14_ROWS, false>(grid, m_x, m_int, m_out, f, st);
         }
         if (e != cudaSuccess) { rc = cuda_fail(e, "fft_tma14_kernel launch"); break; }
         g_launches++;

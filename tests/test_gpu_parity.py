@@ -378,6 +378,7 @@ def test_tma_fused_chunking(gd):                  # more than one 128-transform 
 
 # ----------------------------------------------------------------- FFT2 / FFTN
 @pytest.mark.parametrize("shape", [(2, 3), (3, 5), (64, 32), (300, 7), (8192, 16), (16, 8192), (512, 512),
+                                   (4096, 128), (2048, 96), (3000, 70), (2, 4096, 64), (5000, 33),     # blocked four-step on 4096-point strided lines; tiled gather / scatter around Bluestein lines
                                    (2, 2, 3), (4, 6, 8, 5), (16, 16, 16), (3, 1, 4)])
 def test_fftn_shapes(gd, shape):
     godsp = gd[0]
