@@ -166,3 +166,20 @@ def test_split_1d_shapes():
         D.split_1d(1000, 2)
     with pytest.raises(ValueError):
         D.split_1d(1 << 4, 8)
+
+
+def test_gather_spectrum_layouts():
+    """The two result layouts of the sharded transform map back to the same natural-order spectrum: rank h's [N2][K] slab
+    (separate exchange kernel) and its transposed [K][N2] block (exchange fused into the first line pass)."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "go-dsp_b200"))
+    from godsp import distributed as D
+    n, world = 1 << 10, 4
+    n1, n2, k, w = D.split_1d(n, world)
+    spec = torch.arange(n, dtype=torch.float64).to(torch.complex128)          # X[k1 + N1 k2] at natural index k2 * N1 + k1
+    nat = spec.view(n2, n1)
+    slabs = [nat[:, h * k:(h + 1) * k].contiguous().view(-1) for h in range(world)]
+    blocks = [nat[:, h * k:(h + 1) * k].t().contiguous().view(-1) for h in range(world)]
+    assert torch.equal(D.gather_spectrum(slabs, n), spec)
+    assert torch.equal(D.gather_spectrum(blocks, n, fused=True), spec)
