@@ -7,7 +7,11 @@ cd "$(dirname "$0")/.."
 lib=go-dsp_b200/lib/libgodsp_b200.so
 mkdir -p profiles
 cuobjdump -sass $lib > /tmp/all.sass
-for k in fft_tma14_kernelILi128ELi128ELi0ELb0ELb0 fft_tma14_kernelILi128ELi128ELi1ELb0ELb0 fft_tma14_kernelILi256ELi256ELi0ELb0ELb0 fft_tma14_kernelILi256ELi256ELi1ELb0ELb0 fft_tma14_kernelILi256ELi128ELi0ELb0ELb0 pwelch_bulk_kernel; do
+# kernel name fragments: <LA, LB, MODE, INV, PROF, TW2>; TW2 = 1: outer twiddle on the stores, 2: + stores into the peers' buffers, 3: aux product
+for k in fft_tma14_kernelILi128ELi128ELi0ELb0ELb0ELi0E fft_tma14_kernelILi128ELi128ELi1ELb0ELb0ELi0E fft_tma14_kernelILi256ELi256ELi0ELb0ELb0ELi0E \
+         fft_tma14_kernelILi256ELi256ELi1ELb0ELb0ELi0E fft_tma14_kernelILi256ELi128ELi0ELb0ELb0ELi0E fft_tma14_kernelILi1024ELi512ELi0ELb0ELb0ELi0E \
+         fft_tma14_kernelILi256ELi256ELi1ELb0ELb0ELi1E fft_tma14_kernelILi256ELi256ELi1ELb0ELb0ELi2E fft_tma14_kernelILi256ELi256ELi0ELb0ELb0ELi3E \
+         bluestein_small_kernelILi13ELi1E pwelch_bulk_kernel; do
   awk -v pat="$k" '/Function : /{f=index($0,pat)>0} f' /tmp/all.sass | gzip -9 > profiles/${tag}_sass_${k}.txt.gz
 done
 awk '/Function : /{f=index($0,"fft_tma_fused_kernelILb0ELb0")>0} f' /tmp/all.sass > profiles/${tag}_sass_fft_tma_fused_kernel_forward.txt
