@@ -341,6 +341,7 @@ static int set_option_one(Device& d, const char* key, int64_t value) {
     else if (!strcmp(key, "tma16")) d.use_tma16 = value != 0;
     else if (!strcmp(key, "tma19")) d.use_tma19 = value != 0;
     else if (!strcmp(key, "huge_min_log2n")) { if (value < 19 || value > 25) return (int)invalid_arg("huge_min_log2n out of range"); d.huge_min_log2n = (int)value; }
+    else if (!strcmp(key, "real_widen")) d.real_widen = value != 0;
     else if (!strcmp(key, "bluestein_stream")) d.bluestein_stream = value != 0;
     else if (!strcmp(key, "bluestein_fuse_mul")) d.bluestein_fuse_mul = value != 0;
     else if (!strcmp(key, "bluestein_chunk_mb")) { if (value < 1 || value > 16384) return (int)invalid_arg("bluestein_chunk_mb out of range"); d.bluestein_chunk_bytes = (size_t)value << 20; }

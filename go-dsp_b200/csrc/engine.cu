@@ -1033,6 +1033,17 @@ static Status bluestein_fft(Device& d, const void* in, long long in_dist, cpx* o
     return GD_OK;
 }
 
+// out[t][i] = (in[t][i], 0): batched real -> complex widening (transforms t = blockIdx.y, blockIdx.y + gridDim.y, ...)
+__global__ void widen_real_kernel(const double* __restrict__ in, long long in_dist, cpx* __restrict__ out, long long out_dist, long long n,
+                                  long long batch) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = blockIdx.y; t < batch; t += gridDim.y) {
+        const double* src = in + t * in_dist;
+        cpx* dst = out + t * out_dist;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = make_double2(__ldg(src + i), 0.0);
+    }
+}
+
 Status fft1d(Device& d, const void* in, long long in_dist, cpx* out, long long out_dist, long long n,
              long long batch, bool real_in, int dir, cudaStream_t st) {
     if (n < 1 || batch < 1) return invalid("fft1d: bad size");
@@ -1041,6 +1052,22 @@ Status fft1d(Device& d, const void* in, long long in_dist, cpx* out, long long o
         g_launches++;
         GD_CUDA(cudaGetLastError());
         return GD_OK;
+    }
+    if (is_pow2(n) && real_in && (const void*)in != (const void*)out) {
+        // dsputils.ToComplex (dsputils/dsputils.go:25-31) as its own sweep where the transform that follows has no fused load operator:
+        // the outer four-step (from 2^22 points; above 2^24 the only path) and whole phases of the fused kernels (2^13 .. 2^20)
+        const int lg = ilog2ll(n);
+        const int hmin = batch > 1 ? d.huge_min_log2n - 1 : d.huge_min_log2n;
+        if (lg > 24 || lg >= hmin || (d.real_widen && lg >= 13 && (double)batch * (double)n >= (double)(1LL << 21))) {
+            long long gx = (n + 1023) / 1024;
+            const long long by = batch < 32768 ? batch : 32768;
+            if (gx * by > (long long)d.num_sms * 64) gx = ((long long)d.num_sms * 64 + by - 1) / by;
+            if (gx < 1) gx = 1;
+            widen_real_kernel<<<dim3((unsigned)gx, (unsigned)by, 1), 256, 0, st>>>((const double*)in, in_dist, out, out_dist, n, batch);
+            g_launches++;
+            GD_CUDA(cudaGetLastError());
+            return fft1d(d, out, out_dist, out, out_dist, n, batch, false, dir, st);
+        }
     }
     if (is_pow2(n)) {
         FusedOps ops;

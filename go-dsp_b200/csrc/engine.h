@@ -82,6 +82,7 @@ struct Device {
     void* scratch[SCR_NSLOTS] = {nullptr};
     size_t scratch_bytes[SCR_NSLOTS] = {0};
     size_t pass_scratch_budget = 1ull << 30;    // upper bound of the inter-pass scratch of the two-launch four-step path
+    bool real_widen = true;                     // real input, whole phases of a fused kernel: widen to complex in its own sweep, then the plain transform
     bool bluestein_fuse_mul = true;             // ... with the product with FFT(b) on the stores of the forward transform (fused family sizes)
     bool bluestein_stream = true;               // padded length >= 2^14, at least 2^21 padded points per call: plain transforms + streaming kernels
     size_t bluestein_chunk_bytes = 1ull << 30;  // padded sequences of one Bluestein chunk (between its two transforms)

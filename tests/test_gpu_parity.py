@@ -249,6 +249,29 @@ def test_above_2p24_single_gpu(gd):              # the reference has no length l
     assert "2^30" in L.gd_last_error().decode()
 
 
+@pytest.mark.parametrize("lg", [13, 16, 20, 22, 25])
+def test_real_input_large(gd, lg):               # FFTReal / IFFTReal = transform of dsputils.ToComplex(x): widening sweep + plain transform
+    godsp, capi, L = gd
+    import torch
+    n = 1 << lg
+    r = oracle.fill_splitmix(n, 9)
+    assert rel_l2(godsp.fft.FFTReal(r), oracle.fft_real(r)) <= TOL         # 2^25: failed before (the outer four-step takes no load operator)
+    if lg <= 22:
+        assert rel_l2(godsp.fft.IFFTReal(r), oracle.ifft_real(r)) <= TOL
+    if lg <= 20:                                                            # a batch of real lines on the device, against the complex path's bits
+        b = max(2, (1 << 22) // n) + 1
+        x = torch.empty(b * n, dtype=torch.float64, device="cuda")
+        capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), b * n, 5, 0, None))
+        xc = torch.complex(x, torch.zeros_like(x))
+        y1, y2 = torch.empty(b * n, dtype=torch.complex128, device="cuda"), torch.empty(b * n, dtype=torch.complex128, device="cuda")
+        capi.check(L.gd_fft_batch_r2c_full_dev(x.data_ptr(), y1.data_ptr(), n, b, 1, None))
+        capi.check(L.gd_fft_batch_c2c_dev(xc.data_ptr(), y2.data_ptr(), n, b, 1, None))
+        capi.check(L.gd_stream_sync(None))
+        assert torch.equal(y1, y2)
+        row = y1.view(b, n)[b - 1].cpu().numpy()
+        assert rel_l2(row, oracle.fft_real(x.view(b, n)[b - 1].cpu().numpy())) <= TOL
+
+
 def test_bluestein_padding_lengths(gd):
     L = gd[2]
     for n in (3, 5, 1000, 65537, 1000003):
