@@ -1088,8 +1088,9 @@ Status convolve(Device& d, const cpx* x, const cpx* y, cpx* out, long long n, cu
     GD_TRY(d.ensure_scratch(SCR_B, (size_t)n * sizeof(cpx), (void**)&X));
     GD_TRY(d.ensure_scratch(SCR_C, (size_t)n * sizeof(cpx), (void**)&Y));
     GD_TRY(fft1d(d, y, n, Y, n, n, 1, false, +1, st));
-    if (is_pow2(n) && n >= 2 && n <= (1LL << 24)) {
-        // FFT(x) * FFT(y) (fft.go:63-66) fused into the store of FFT(x): ST_MULAUX with aux = FFT(y)
+    if (is_pow2(n) && n >= 2 && n < (1LL << d.huge_min_log2n)) {
+        // FFT(x) * FFT(y) (fft.go:63-66) fused into the store of FFT(x): ST_MULAUX with aux = FFT(y); from 2^22 points the plain
+        // transform (outer four-step) and a product sweep are faster than the two passes that take the operator
         FusedOps f;
         f.st_flags = ST_MULAUX; f.aux_out = Y;
         GD_TRY(fft_pow2(d, x, n, X, n, ilog2ll(n), 1, f, st));

@@ -278,7 +278,7 @@ def test_bluestein_padding_lengths(gd):
         assert L.gd_bluestein_padded_len(n) == oracle.bluestein_padded_len(n)
 
 
-@pytest.mark.parametrize("n", [8, 48, 1000, 4096, 1 << 15])
+@pytest.mark.parametrize("n", [8, 48, 1000, 4096, 1 << 15, 1 << 21, 1 << 22, 5000])      # 2^22: plain transforms + product sweep
 def test_convolve(gd, n):
     godsp = gd[0]
     x, y = oracle.splitmix_complex(n, 1), oracle.splitmix_complex(n, 2)

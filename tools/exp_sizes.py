@@ -18,7 +18,8 @@ capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), TOTAL * 2, 3, 0, None)); capi.ch
 st = torch.cuda.Stream(); sp = st.cuda_stream
 args = sys.argv[1:]
 ONE = "--one" in args          # a single transform per call (latency of one large transform) instead of 2^28 points
-args = [a for a in args if a != "--one"]
+REAL = "--real" in args        # float64 input (fft.FFTReal = the transform of dsputils.ToComplex(x)); the roofline is then 24 B per point
+args = [a for a in args if a not in ("--one", "--real")]
 opts = ""
 if args and "=" in args[0]:
     opts = args.pop(0)
@@ -28,7 +29,10 @@ sizes = [int(a[1:]) if a.startswith("n") else 1 << int(a) for a in args] or [1 <
 import time
 for n in sizes:
     batch = 1 if ONE else max(1, TOTAL // n)
-    fn = lambda: capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, batch, 1, sp))
+    if REAL:
+        fn = lambda: capi.check(L.gd_fft_batch_r2c_full_dev(x.data_ptr(), y.data_ptr(), n, batch, 1, sp))
+    else:
+        fn = lambda: capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, batch, 1, sp))
     torch.cuda.synchronize()
     with torch.cuda.stream(st):
         for _ in range(2): fn()
@@ -39,4 +43,4 @@ for n in sizes:
     ms = min(ts)
     torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); host_ms = (time.perf_counter() - t0) * 1e3; torch.cuda.synchronize()
     gs = n * batch / ms / 1e6
-    print(json.dumps({"opts": opts, "host_issue_ms": round(host_ms, 3), "n": n, "batch": batch, "ms": round(ms, 4), "gs": round(gs, 2), "hbm_frac": round(gs * 32 / PEAK, 3)}), flush=True)
+    print(json.dumps({"opts": opts, "host_issue_ms": round(host_ms, 3), "n": n, "batch": batch, "ms": round(ms, 4), "gs": round(gs, 2), "hbm_frac": round(gs * (24 if REAL else 32) / PEAK, 3), **({"real_input": True} if REAL else {})}), flush=True)
