@@ -56,7 +56,7 @@ capi.check(L.gd_fill_splitmix_dev(x.data_ptr(), 2 * n, 2, 0, sp))
 capi.check(L.gd_plan_warm(n))
 med, best = timed(lambda: capi.check(L.gd_fft_batch_c2c_dev(x.data_ptr(), y.data_ptr(), n, 1, 1, sp)), flush=flush)
 out["C2_bluestein_1000003"] = {"median_ms": med, "best_ms": best, "la": int(L.gd_bluestein_padded_len(n)),
-                               "note": "chirp + FFT(b) cached per N; 2 fused 2^21 transforms per call"}
+                               "note": "chirp + FFT(b) cached per N; prep, forward 2^21 transform, product, inverse transform, post (plain transforms between streaming kernels)"}
 med, best = timed(lambda: capi.check(L.gd_fft_batch_r2c_full_dev(x.data_ptr(), y.data_ptr(), n, 1, 1, sp)), flush=flush)
 out["C2_fftreal_1000003"] = {"median_ms": med, "best_ms": best}
 
